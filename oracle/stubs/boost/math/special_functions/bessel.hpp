@@ -1,0 +1,18 @@
+/* Boost.Math is absent from this image.  The reference needs it only for the
+ * `dipolar_rep` Jastrow (dmc/wavefunction/jastrows/jastrowDipolar.h:31-62), which no
+ * BASELINE config uses.  This stand-in lets the unmodified reference main.cpp /
+ * jastrowDipolar.cpp compile into oracle/_ref; calling it aborts ("parity unpinned" for
+ * that one Jastrow).  TEST INFRASTRUCTURE, not product code. */
+#ifndef QMC4_ORACLE_BOOST_BESSEL_STUB
+#define QMC4_ORACLE_BOOST_BESSEL_STUB
+#include <cstdio>
+#include <cstdlib>
+namespace boost { namespace math {
+template <class T1, class T2> inline double cyl_bessel_k(T1, T2)
+{
+  std::fprintf(stderr, "oracle/_ref: boost::math::cyl_bessel_k is not available (dipolar_rep unsupported)\n");
+  std::abort();
+  return 0.;
+}
+}}
+#endif
