@@ -1,0 +1,1277 @@
+// capi.cu — the C ABI declared in include/qmc4_b200.h: context, term-list compiler ("plan"),
+// HBM buffers, step sequencing on one CUDA stream, NCCL plumbing.  No physics here except the
+// derived-coefficient formulas of the reference's Jastrow constructors.
+#include "../../include/qmc4_b200.h"
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace qmc;
+
+// ---- NCCL, resolved at run time (the library also has to load on boxes without NCCL) ----------
+extern "C" {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+}
+namespace {
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_t, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load(std::string &err)
+  {
+    if (h) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names)
+      {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+      }
+    if (!h)
+      {
+        err = std::string("cannot load NCCL: ") + dlerror();
+        return false;
+      }
+#define QMC_SYM(field, name)                                              \
+  field = reinterpret_cast<decltype(field)>(dlsym(h, name));              \
+  if (!field)                                                             \
+    {                                                                     \
+      err = std::string("NCCL symbol missing: ") + name;                  \
+      return false;                                                       \
+    }
+    QMC_SYM(GetUniqueId, "ncclGetUniqueId")
+    QMC_SYM(CommInitRank, "ncclCommInitRank")
+    QMC_SYM(CommDestroy, "ncclCommDestroy")
+    QMC_SYM(AllReduce, "ncclAllReduce")
+    QMC_SYM(AllGather, "ncclAllGather")
+    QMC_SYM(Send, "ncclSend")
+    QMC_SYM(Recv, "ncclRecv")
+    QMC_SYM(GroupStart, "ncclGroupStart")
+    QMC_SYM(GroupEnd, "ncclGroupEnd")
+    QMC_SYM(GetErrorString, "ncclGetErrorString")
+#undef QMC_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int NCCL_INT32 = 2, NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+std::string g_create_error;
+} // namespace
+
+// ---- context ----------------------------------------------------------------------------------
+struct WfTerm { int kind; std::vector<int> sets; RadialFn J; double hs; };
+struct PotTerm { int kind; std::vector<int> sets; std::vector<double> p; };
+struct EstTerm { int kind; std::vector<int> sets; int bins; double minx, maxx; std::vector<double> extra; };
+
+struct qmc_ctx {
+  int device = 0;
+  int sms = 0, max_smem = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  double lBox[3];
+  std::vector<int> N;
+  std::vector<WfTerm> wf;
+  std::vector<PotTerm> pot;
+  std::vector<EstTerm> est;
+  std::vector<double> coefpool;
+  bool planned = false;
+  Plan plan;
+  DmcParams dmc;
+  int ksel = KSEL_GENERIC;
+  bool has_hist = false;
+  LaunchCfg cfg;
+  int64_t cap = 0;
+  WalkerBuf buf[2] = {};
+  int cur = 0;
+  int *parent = nullptr, *n_desc = nullptr;
+  double *partials = nullptr;
+  Ctl *ctl = nullptr;
+  double *coef = nullptr;
+  double *hist = nullptr, *hist_out = nullptr;
+  int n_partials = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double device_ms = 0;
+  long sample_phase = 0;
+  // scratch for host-pointer entry points
+  double *scr = nullptr;
+  size_t scr_bytes = 0;
+  int *scr_i = nullptr;
+  size_t scr_i_bytes = 0;
+  // multi rank
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  double *slab_send = nullptr, *slab_recv = nullptr;
+  size_t slab_bytes = 0;
+  long launches = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                              \
+  do                                                                                          \
+    {                                                                                         \
+      cudaError_t e__ = (call);                                                               \
+      if (e__ != cudaSuccess)                                                                 \
+        {                                                                                     \
+          c->err = std::string(#call) + ": " + cudaGetErrorString(e__);                       \
+          return 1;                                                                           \
+        }                                                                                     \
+    }                                                                                         \
+  while (0)
+#define NK(call)                                                                              \
+  do                                                                                          \
+    {                                                                                         \
+      int e__ = (call);                                                                       \
+      if (e__ != 0)                                                                           \
+        {                                                                                     \
+          c->err = std::string(#call) + ": " + g_nccl.GetErrorString(e__);                    \
+          return 1;                                                                           \
+        }                                                                                     \
+    }                                                                                         \
+  while (0)
+
+int fail(qmc_ctx *c, const std::string &m)
+{
+  c->err = m;
+  return 1;
+}
+
+// Derived coefficients, following the reference constructors (file:line in each case).
+int derive_radial(qmc_ctx *c, int kind, const double *p, int np, RadialFn &J)
+{
+  memset(&J, 0, sizeof J);
+  J.kind = kind;
+  auto need = [&](int n) { return np >= n; };
+  switch (kind)
+    {
+    case QMC_J_GAUSSIAN: /* jastrowGaussian.h:12-18 */
+      if (!need(1)) return fail(c, "gaussian: {alpha}");
+      J.p[0] = p[0];
+      return 0;
+    case QMC_J_GAUSSGAUSS: /* jastrowGaussGauss.cpp:5-17: alpha = 1/(2 r0^2) */
+      {
+        if (!need(2)) return fail(c, "gaussiangaussian: {r0,u0}");
+        const double alpha = 1. / (2 * p[0] * p[0]);
+        J.p[0] = alpha;
+        J.p[1] = p[1];
+        const long double a = -(long double)alpha;
+        J.p[2] = (double)(a * 1.442695040888963407359924681001892137L);
+        const long double c_ = 0.693147180559945309417232121458176568L / a;
+        double hi = (double)c_;
+        uint64_t bits;
+        memcpy(&bits, &hi, 8);
+        bits &= 0xffffffff00000000ull;          /* 21 significant bits: n*hi exact for |n| < 2^31 */
+        memcpy(&hi, &bits, 8);
+        J.p[3] = hi;
+        J.p[4] = (double)(c_ - (long double)hi);
+        static const double T[11] = {1.0, 1.0, 0.5, 0.16666666666648303, 0.041666666666651364, 0.008333333353717156,
+                                     0.0013888888905871347, 0.0001984120875699232, 2.4801536409064087e-05,
+                                     2.7625102005388108e-06, 2.761379555451986e-07};
+        long double ap = 1;
+        for (int j = 1; j <= 10; ++j)
+          {
+            ap *= a;
+            J.p[4 + j] = (double)((long double)T[j] * ap);
+          }
+        return 0;
+      }
+    case QMC_J_SQUAREWELL: /* jastrowSquareWell.cpp:5-44 ; JSON ctor: (V0,R0,Rm,alpha,aInverse,cut_off*2) */
+      {
+        if (!need(6)) return fail(c, "squareWell: {V0,R0,Rm,alpha,aInverse,cut_off}");
+        const double V0 = p[0], R0 = p[1], Rm = p[2], alpha = p[3], aInv = p[4], lBox = p[5] * 2;
+        const double K0 = std::sqrt(V0), half = lBox / 2.;
+        const double A = std::sin(K0 * R0) / (1 - R0 * aInv);
+        const double C = -A / (Rm * Rm * alpha * (std::exp(-alpha * (lBox - Rm)) - std::exp(-alpha * Rm)));
+        const double B = A * (1 / Rm - aInv) - C * (std::exp(-alpha * Rm) + std::exp(-alpha * (lBox - Rm)));
+        if (B + C * 2 * exp(-alpha * half) < 0) return fail(c, "Jastrow cannot be negative");
+        J.p[0] = R0; J.p[1] = Rm; J.p[2] = half; J.p[3] = K0; J.p[4] = aInv; J.p[5] = alpha; J.p[6] = lBox;
+        J.p[7] = B; J.p[8] = C; J.p[9] = std::log(B + C * 2 * std::exp(-alpha * half));
+        return 0;
+      }
+    case QMC_J_SQUAREWELL_BOUND: /* jastrowSquareWell.cpp:46-95 ; JSON ctor: (V0,R0,Rm,cut_off*2,aInverse,eb,alpha) */
+      {
+        if (!need(7)) return fail(c, "squareWellBoundState: {V0,R0,Rm,cut_off,aInverse,eb,alpha}");
+        const double V0 = p[0], R0 = p[1], Rm = p[2], lBox = p[3] * 2., eb = p[5], alpha = p[6];
+        const double m = 0.5, K0 = sqrt(2 * m * (V0 - eb)), half = lBox / 2., ec = sqrt(2 * m * eb);
+        const double A = exp(-ec * R0) / sin(K0 * R0);
+        const double C = exp(-ec * Rm) * (1. / (Rm * Rm) + ec / Rm) / (alpha * (exp(-alpha * Rm) - exp(-alpha * (lBox - Rm))));
+        const double B = -C * (exp(-alpha * Rm) + exp(-alpha * (lBox - Rm))) + exp(-ec * Rm) / Rm;
+        if (B + C * 2 * exp(-alpha * half) < 0) return fail(c, "Jastrow cannot be negative");
+        J.p[0] = R0; J.p[1] = Rm; J.p[2] = half; J.p[3] = K0; J.p[4] = log(A); J.p[5] = ec; J.p[6] = alpha; J.p[7] = lBox;
+        J.p[8] = B; J.p[9] = C; J.p[10] = log(B + C * 2 * exp(-alpha * half));
+        return 0;
+      }
+    case QMC_J_HARDSPHEREGAUSS: /* jastrowHardSphereGauss.cpp:4-16 */
+      {
+        if (!need(3)) return fail(c, "hardSphereGauss: {a,Rm,D}");
+        const double a = p[0], Rm = p[1], d = p[2];
+        const double alpha = a / (Rm * (Rm - a) * 2 * (d - Rm));
+        const double C = (1 - a / Rm) * exp(alpha * (Rm - d) * (Rm - d));
+        J.p[0] = Rm; J.p[1] = a; J.p[2] = d; J.p[3] = alpha; J.p[4] = log(C);
+        return 0;
+      }
+    case QMC_J_HARDSPHERE: /* jastrowHardSphereGauss.cpp:18-32 */
+      {
+        if (!need(3)) return fail(c, "hardSphere: {a,k,cut_off}");
+        J.p[0] = p[0]; J.p[1] = p[2]; J.p[2] = p[2] / sin(p[1] * (p[2] - p[0])); J.p[3] = p[1];
+        return 0;
+      }
+    case QMC_J_POSCHTELLER: /* jastrowPoschTeller.cpp:4-24 ; longDistanceConstant has no log (sic) */
+      {
+        if (!need(5)) return fail(c, "poschTeller: {R0,C,alpha,Rm,cut_off}");
+        const double R0 = p[0], C = p[1], alpha = p[2], Rm = p[3], lBox = p[4] * 2.;
+        J.p[0] = Rm; J.p[1] = lBox / 2.; J.p[2] = 1 / R0; J.p[3] = alpha; J.p[4] = lBox; J.p[5] = C;
+        J.p[6] = 2 * C * exp(-alpha * lBox / 2.);
+        return 0;
+      }
+    case QMC_J_BSPLINE: /* jastrowSpline.cpp:20-78 */
+      {
+        if (!need(3 + 4)) return fail(c, "bSpline: {stepSize,valueRight,derivativeRight,coefficients...}");
+        const int nc = np - 3;
+        J.ncoef = nc;
+        J.coef_off = (int)c->coefpool.size();
+        for (int i = 0; i < nc; ++i) c->coefpool.push_back(p[3 + i]);
+        J.p[0] = 1. / p[0];
+        J.p[1] = (nc - 3) * p[0];
+        J.p[2] = p[1];
+        J.p[3] = p[2];
+        return 0;
+      }
+    default:
+      return fail(c, "unknown jastrow kind " + std::to_string(kind));
+    }
+}
+
+// largest double t with sqrt(t) <= R0 (sqrt correctly rounded and monotone), so that
+//   r2 <= t   <=>   sqrt(r2) <= R0   bit for bit (potentialFunctors.h:9,26 compare the rounded norm)
+double step_threshold(double R0)
+{
+  if (!(R0 > 0)) return -1.0;
+  double t = R0 * R0;
+  while (std::sqrt(t) > R0) t = std::nextafter(t, 0.0);
+  while (std::sqrt(std::nextafter(t, INFINITY)) <= R0) t = std::nextafter(t, INFINITY);
+  return t;
+}
+
+bool same_pair(int a0, int a1, int b0, int b1) { return (a0 == b0 && a1 == b1) || (a0 == b1 && a1 == b0); }
+
+int build_plan(qmc_ctx *c)
+{
+  Plan &P = c->plan;
+  memset(&P, 0, sizeof P);
+  const int S = (int)c->N.size();
+  P.nSpecies = S;
+  int off = 0;
+  for (int s = 0; s < S; ++s)
+    {
+      P.N[s] = c->N[s];
+      P.off[s] = off;
+      off += 3 * c->N[s];
+      P.Ntot += c->N[s];
+    }
+  P.dofs = off;
+  for (int d = 0; d < 3; ++d)
+    {
+      P.L[d] = c->lBox[d];
+      P.Linv[d] = 1. / c->lBox[d];       /* geometry.h:39 */
+    }
+  auto set_ok = [&](int s) { return s >= 0 && s < S; };
+  // estimators first (pair passes refer to them)
+  int hoff = 0;
+  for (size_t e = 0; e < c->est.size(); ++e)
+    {
+      if (P.nest >= MAX_EST) return fail(c, "too many estimators");
+      const EstTerm &E = c->est[e];
+      Estimator &D = P.est[P.nest++];
+      D.kind = E.kind;
+      D.setA = E.sets[0];
+      D.setB = E.sets.size() > 1 ? E.sets[1] : E.sets[0];
+      if (!set_ok(D.setA) || !set_ok(D.setB)) return fail(c, "estimator: invalid set");
+      D.bins = E.bins;
+      D.offset = hoff;
+      hoff += E.bins;
+      D.minx = E.minx;
+      D.maxx = E.maxx;
+      const double dx = (E.maxx - E.minx) / E.bins;       /* accumulators.h:108 */
+      D.dxinv = 1. / dx;
+      if (E.kind == QMC_EST_PAIRCORRELATION)
+        { /* pairCorrelation.cpp:41-59 */
+          double nf = std::pow(c->lBox[0], 3) / (dx * 4 * M_PI * P.N[D.setA] * P.N[D.setB]);
+          D.norm = (D.setA == D.setB) ? 2 * nf : nf;
+        }
+      else if (E.kind == QMC_EST_TRIMERCORRELATION_UNDIS)
+        { /* trimerCorrelation.cpp:128-143 */
+          const double NA = P.N[D.setA];
+          D.norm = 1 / (dx * 4 * M_PI * NA * NA * NA);
+        }
+      else if (E.kind == QMC_EST_STRUCTUREFACTOR)
+        { /* structureFactor.cpp:8-40 */
+          if (E.extra.size() < 3) return fail(c, "structureFactor: extra={maxq,lBox,channel}");
+          const double qMax = E.extra[0], lb = E.extra[1];
+          double dq = int(qMax / (2 * M_PI * E.bins / lb)) * 2 * M_PI / lb;
+          if (dq == 0) dq = 2 * M_PI / lb;
+          D.q0 = 2 * M_PI / lb;
+          D.dq = dq;
+          D.channel = (int)E.extra[2];
+          D.norm = 1;
+        }
+      else return fail(c, "unknown estimator kind");
+    }
+  P.hist_stride = hoff;
+  // wavefunction terms
+  for (const WfTerm &w : c->wf)
+    {
+      for (int s : w.sets)
+        if (!set_ok(s)) return fail(c, "wavefunction term: invalid set");
+      if (w.kind == QMC_WF_JASTROW1B)
+        {
+          if (P.n1b >= MAX_ONEBODY) return fail(c, "too many one-body terms");
+          OneBodyTerm &T = P.t1[P.n1b++];
+          T.set = w.sets[0];
+          T.J = w.J;
+        }
+      else if (w.kind == QMC_WF_JASTROW2B_UNDIS || w.kind == QMC_WF_JASTROW2B_DIS)
+        {
+          if (w.sets.size() < 2) return fail(c, "two-body jastrow needs sets={A,B}");
+          if (w.kind == QMC_WF_JASTROW2B_UNDIS && w.sets[0] != w.sets[1])
+            return fail(c, "setA != setB in undistinguishable two body jastrow");   /* jastrowWavefunctionTwoBody.h:100 */
+          if (w.kind == QMC_WF_JASTROW2B_DIS && w.sets[0] == w.sets[1])
+            return fail(c, "setA == setB in distinguishable two body jastrow");     /* jastrowWavefunctionTwoBody.h:11 */
+          if (P.n2b >= MAX_PAIRPASS) return fail(c, "too many pair passes");
+          PairPass &T = P.p2[P.n2b++];
+          T.setA = w.sets[0];
+          T.setB = w.sets[1];
+          T.vkind = V_NONE;
+          T.hist = -1;
+          T.J = w.J;
+        }
+      else if (w.kind == QMC_WF_JASTROW3B_UNDIS)
+        {
+          if (P.n3b >= MAX_TRIPLETPASS) return fail(c, "too many triplet passes");
+          TripletPass &T = P.p3[P.n3b++];
+          T.set = w.sets[0];
+          T.hist = -1;
+          T.J = w.J;
+          if (w.hs >= 0)
+            {
+              T.has_constraint = 1;
+              T.hs_R0 = w.hs;
+            }
+        }
+      else return fail(c, "unknown wavefunction kind");
+    }
+  // potentials
+  for (const PotTerm &v : c->pot)
+    {
+      for (int s : v.sets)
+        if (!set_ok(s)) return fail(c, "potential term: invalid set");
+      if (v.kind == QMC_POT_HARMONIC1B)
+        {
+          OneBodyTerm *T = nullptr;
+          for (int t = 0; t < P.n1b; ++t)
+            if (P.t1[t].set == v.sets[0] && !P.t1[t].has_pot) T = &P.t1[t];
+          if (!T)
+            {
+              if (P.n1b >= MAX_ONEBODY) return fail(c, "too many one-body terms");
+              T = &P.t1[P.n1b++];
+              T->set = v.sets[0];
+              T->J.kind = J_NONE;
+            }
+          T->has_pot = 1;
+          T->half_omega2 = 0.5 * v.p[0] * v.p[0];      /* potential.cpp:29 */
+        }
+      else if (v.kind == QMC_POT_THREEBODY_UNDIS_SQUAREWELL || v.kind == QMC_POT_THREEBODY_UNDIS_BARRIER)
+        {
+          TripletPass *T = nullptr;
+          for (int t = 0; t < P.n3b; ++t)
+            if (P.p3[t].set == v.sets[0] && !P.p3[t].has_pot) T = &P.p3[t];
+          if (!T)
+            {
+              if (P.n3b >= MAX_TRIPLETPASS) return fail(c, "too many triplet passes");
+              T = &P.p3[P.n3b++];
+              T->set = v.sets[0];
+              T->hist = -1;
+              T->J.kind = J_NONE;
+            }
+          T->has_pot = 1;
+          T->v_R0 = v.p[0];
+          T->v_val = (v.kind == QMC_POT_THREEBODY_UNDIS_SQUAREWELL) ? -v.p[1] : v.p[1];   /* potentialFunctors.h:9,26 */
+        }
+      else
+        {
+          if (v.sets.size() < 2) return fail(c, "two-body potential needs sets={A,B}");
+          int vk = V_NONE;
+          double thr = 0, val = 0;
+          switch (v.kind)
+            {
+            case QMC_POT_SQUAREWELL2B: /* params {V0,R0}: -count(d<=R0)*V0, potential.cpp:57-65 */
+              vk = V_STEP; thr = step_threshold(v.p[1]); val = -v.p[0]; break;
+            case QMC_POT_TWOBODY_SQUAREWELL: /* params {R0,V0} */
+              vk = V_STEP; thr = step_threshold(v.p[0]); val = -v.p[1]; break;
+            case QMC_POT_TWOBODY_BARRIER:
+              vk = V_STEP; thr = step_threshold(v.p[0]); val = v.p[1]; break;
+            case QMC_POT_DIPOLAR2B:
+              vk = V_DIPOLAR; val = v.p[0]; break;
+            case QMC_POT_POSCHTELLER2B:
+              vk = V_POSCHTELLER; val = 1 / v.p[0]; break;      /* alpha = 1/R0, potential.cpp:121 */
+            default: return fail(c, "unknown potential kind");
+            }
+          PairPass *T = nullptr;
+          for (int t = 0; t < P.n2b; ++t)
+            if (same_pair(P.p2[t].setA, P.p2[t].setB, v.sets[0], v.sets[1]) && P.p2[t].vkind == V_NONE && !T) T = &P.p2[t];
+          if (!T)
+            {
+              if (P.n2b >= MAX_PAIRPASS) return fail(c, "too many pair passes");
+              T = &P.p2[P.n2b++];
+              T->setA = v.sets[0];
+              T->setB = v.sets[1];
+              T->hist = -1;
+              T->J.kind = J_NONE;
+            }
+          T->vkind = vk;
+          T->v_thr2 = thr;
+          T->v_val = val;
+        }
+    }
+  // estimators attach to passes
+  c->has_hist = P.nest > 0;
+  int max_sf_bins = 0;
+  for (int e = 0; e < P.nest; ++e)
+    {
+      Estimator &D = P.est[e];
+      if (D.kind == QMC_EST_PAIRCORRELATION)
+        {
+          PairPass *T = nullptr;
+          for (int t = 0; t < P.n2b; ++t)
+            if (same_pair(P.p2[t].setA, P.p2[t].setB, D.setA, D.setB) && P.p2[t].hist < 0 && !T) T = &P.p2[t];
+          if (!T)
+            {
+              if (P.n2b >= MAX_PAIRPASS) return fail(c, "too many pair passes");
+              T = &P.p2[P.n2b++];
+              T->setA = D.setA;
+              T->setB = D.setB;
+              T->vkind = V_NONE;
+              T->J.kind = J_NONE;
+            }
+          T->hist = e;
+        }
+      else if (D.kind == QMC_EST_TRIMERCORRELATION_UNDIS)
+        {
+          TripletPass *T = nullptr;
+          for (int t = 0; t < P.n3b; ++t)
+            if (P.p3[t].set == D.setA && P.p3[t].hist < 0 && !T) T = &P.p3[t];
+          if (!T)
+            {
+              if (P.n3b >= MAX_TRIPLETPASS) return fail(c, "too many triplet passes");
+              T = &P.p3[P.n3b++];
+              T->set = D.setA;
+              T->J.kind = J_NONE;
+            }
+          T->hist = e;
+        }
+      else if (D.kind == QMC_EST_STRUCTUREFACTOR) max_sf_bins = std::max(max_sf_bins, D.bins);
+    }
+  // put a pass with a specialised kernel first
+  auto spec = [&](const PairPass &T) -> int {
+    if (T.J.kind == J_GAUSSGAUSS && T.vkind == V_STEP) return KSEL_GG_STEP;
+    if (T.J.kind == J_GAUSSGAUSS && T.vkind == V_NONE) return KSEL_GG_NONE;
+    if (T.J.kind == J_GAUSSIAN && T.vkind == V_NONE) return KSEL_GAUSS_NONE;
+    return (int)KSEL_GENERIC;
+  };
+  c->ksel = KSEL_GENERIC;
+  for (int t = 0; t < P.n2b; ++t)
+    if (spec(P.p2[t]) != KSEL_GENERIC)
+      {
+        std::swap(P.p2[0], P.p2[t]);
+        c->ksel = spec(P.p2[0]);
+        break;
+      }
+  if (const char *e = getenv("QMC4_FORCE_GENERIC"))
+    if (atoi(e)) c->ksel = KSEL_GENERIC;
+  // work decomposition: warps per walker group from the tile count of the largest pair pass
+  int maxN = 1;
+  for (int s = 0; s < S; ++s) maxN = std::max(maxN, P.N[s]);
+  const int nb = (maxN + 31) / 32, tiles = nb * (nb + 1) / 2;
+  int wpw = tiles <= 3 ? 1 : tiles <= 10 ? 2 : tiles <= 36 ? 4 : 8;
+  if (P.n3b > 0) wpw = 8;
+  if (const char *e = getenv("QMC4_WPW"))
+    {
+      int v = atoi(e);
+      if (v == 1 || v == 2 || v == 4 || v == 8) wpw = v;
+    }
+  int tab = 0;
+  for (int t = 0; t < P.n3b; ++t)
+    {
+      const int n = P.N[P.p3[t].set];
+      tab = std::max(tab, 2 * (n * (n - 1) / 2));
+    }
+  P.needs_pair_table = tab;
+  P.aux_doubles = max_sf_bins * 2 * wpw;
+  size_t group_doubles = (size_t)P.dofs * (1 + wpw) + (wpw * 4 + 8) + tab + P.aux_doubles;
+  group_doubles = (group_doubles + 1) & ~(size_t)1;
+  c->cfg.block = 256;
+  c->cfg.nwarps_per_group = wpw;
+  c->cfg.groups_per_cta = 8 / wpw;
+  c->cfg.smem = group_doubles * 8 * c->cfg.groups_per_cta;
+  if ((int)c->cfg.smem > c->max_smem)
+    return fail(c, "configuration needs " + std::to_string(c->cfg.smem) + " B of shared memory per CTA (limit " +
+                       std::to_string(c->max_smem) + "): too many particles for this build");
+  return 0;
+}
+
+int ensure_scratch(qmc_ctx *c, size_t bytes, size_t ibytes)
+{
+  if (bytes > c->scr_bytes)
+    {
+      if (c->scr) cudaFree(c->scr);
+      c->scr = nullptr;
+      CK(cudaMalloc(&c->scr, bytes));
+      c->scr_bytes = bytes;
+    }
+  if (ibytes > c->scr_i_bytes)
+    {
+      if (c->scr_i) cudaFree(c->scr_i);
+      c->scr_i = nullptr;
+      CK(cudaMalloc(&c->scr_i, ibytes));
+      c->scr_i_bytes = ibytes;
+    }
+  return 0;
+}
+
+int grid_for(qmc_ctx *c, int64_t nW)
+{
+  // persistent-style grid: a multiple of the SM count (resident CTAs per SM bounded by shared memory)
+  int per_sm = std::max(1, std::min(8, (int)(c->max_smem / std::max<size_t>(c->cfg.smem, 1))));
+  per_sm = std::min(per_sm, 2048 / c->cfg.block);
+  if (const char *e = getenv("QMC4_CTAS_PER_SM"))
+    {
+      int v = atoi(e);
+      if (v >= 1 && v <= 8) per_sm = v;
+    }
+  int64_t want = (nW + c->cfg.groups_per_cta - 1) / c->cfg.groups_per_cta;
+  int64_t g = std::min<int64_t>(want, (int64_t)c->sms * per_sm);
+  return (int)std::max<int64_t>(g, 1);
+}
+
+int allreduce_sums(qmc_ctx *c)
+{
+  if (c->nranks > 1)
+    {
+      NK(g_nccl.AllReduce(c->ctl->lsum, c->ctl->gsum, 2 + MAX_RANKS, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+      CK(launch_finalize_shift(c->stream, c->dmc, c->ctl));
+      c->launches += 1;
+    }
+  return 0;
+}
+
+StepArgs make_step_args(qmc_ctx *c, int accumulate)
+{
+  StepArgs a;
+  memset(&a, 0, sizeof a);
+  a.in = c->buf[c->cur];
+  a.out = c->buf[c->cur ^ 1];
+  a.parent = c->parent;
+  a.n_desc = c->n_desc;
+  a.partials = c->partials;
+  a.ctl = c->ctl;
+  a.coef = c->coef;
+  a.hist = (accumulate && c->has_hist) ? c->hist : nullptr;
+  a.accumulate = accumulate;
+  a.cap = (int)c->cap;
+  return a;
+}
+
+int one_step(qmc_ctx *c, int accumulate, const TraceDev *tr)
+{
+  StepArgs a = make_step_args(c, accumulate);
+  if (tr) a.trace = *tr;
+  const bool hist = accumulate && c->has_hist;
+  CK(launch_propagate(c->ksel, hist, c->cfg, c->stream, c->plan, c->dmc, a));
+  CK(launch_scan(c->stream, c->dmc, a, c->n_partials, c->nranks > 1, 0));
+  c->launches += 2;
+  c->cur ^= 1;
+  return allreduce_sums(c);
+}
+
+} // namespace
+
+__global__ void gather_kernel(WalkerBuf buf, const int *parent, int dofs, int count, double *R, double *E)
+{
+  const int w = blockIdx.x;
+  if (w >= count) return;
+  const int p = parent[w];
+  for (int k = threadIdx.x; k < dofs; k += blockDim.x) R[(size_t)w * dofs + k] = buf.R[(size_t)p * dofs + k];
+  if (threadIdx.x == 0 && E) E[w] = buf.E[p];
+}
+
+// ================================================================================================
+extern "C" {
+
+int qmc_abi_version(void) { return QMC4_B200_ABI_VERSION; }
+
+const char *qmc_last_error(const qmc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, const int *N)
+{
+  if (!out) return 1;
+  *out = nullptr;
+  if (nSpecies < 1 || nSpecies > MAX_SPECIES)
+    {
+      g_create_error = "nSpecies must be in 1.." + std::to_string(MAX_SPECIES);
+      return 1;
+    }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    {
+      g_create_error = std::string("qmc4_b200 needs a CUDA device (no CPU fallback): ") + cudaGetErrorString(e);
+      return 1;
+    }
+  if (device < 0 || device >= ndev)
+    {
+      g_create_error = "invalid device index";
+      return 1;
+    }
+  qmc_ctx *c = new qmc_ctx;
+  c->device = device;
+  for (int d = 0; d < 3; ++d) c->lBox[d] = lBox[d];
+  c->N.assign(N, N + nSpecies);
+  auto bail = [&](const std::string &m) {
+    g_create_error = m;
+    delete c;
+    return 1;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  if (prop.major < 10) return bail(std::string("qmc4_b200 is built for sm_100a only; device is ") + prop.name);
+  c->sms = prop.multiProcessorCount;
+  c->max_smem = (int)prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  if ((e = configure_kernels(c->max_smem)) != cudaSuccess) return bail(std::string("kernel image: ") + cudaGetErrorString(e));
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+  if ((e = cudaMalloc(&c->ctl, sizeof(Ctl))) != cudaSuccess) return bail(cudaGetErrorString(e));
+  cudaMemset(c->ctl, 0, sizeof(Ctl));
+  memset(&c->dmc, 0, sizeof c->dmc);
+  c->dmc.nranks = 1;
+  *out = c;
+  return 0;
+}
+
+void qmc_destroy(qmc_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int b = 0; b < 2; ++b)
+    {
+      cudaFree(c->buf[b].R);
+      cudaFree(c->buf[b].F);
+      cudaFree(c->buf[b].logpsi);
+      cudaFree(c->buf[b].E);
+    }
+  cudaFree(c->parent);
+  cudaFree(c->n_desc);
+  cudaFree(c->partials);
+  cudaFree(c->ctl);
+  cudaFree(c->coef);
+  cudaFree(c->hist);
+  cudaFree(c->hist_out);
+  cudaFree(c->scr);
+  cudaFree(c->scr_i);
+  cudaFree(c->slab_send);
+  cudaFree(c->slab_recv);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int qmc_add_wavefunction_term(qmc_ctx *c, int wf_kind, const int *sets, int nsets, int jastrow_kind,
+                              const double *params, int nparams, double hardSphereRadius)
+{
+  if (!c) return 1;
+  if (c->planned) return fail(c, "terms must be added before qmc_set_dmc");
+  if (nsets < 1) return fail(c, "sets missing");
+  WfTerm t;
+  t.kind = wf_kind;
+  t.sets.assign(sets, sets + nsets);
+  t.hs = hardSphereRadius;
+  if (derive_radial(c, jastrow_kind, params, nparams, t.J)) return 1;
+  c->wf.push_back(t);
+  return 0;
+}
+
+int qmc_add_potential_term(qmc_ctx *c, int pot_kind, const int *sets, int nsets, const double *params, int nparams)
+{
+  if (!c) return 1;
+  if (c->planned) return fail(c, "terms must be added before qmc_set_dmc");
+  if (nsets < 1) return fail(c, "sets missing");
+  const int need = (pot_kind == QMC_POT_HARMONIC1B || pot_kind == QMC_POT_DIPOLAR2B || pot_kind == QMC_POT_POSCHTELLER2B) ? 1 : 2;
+  if (nparams < need) return fail(c, "potential: missing parameters");
+  PotTerm t;
+  t.kind = pot_kind;
+  t.sets.assign(sets, sets + nsets);
+  t.p.assign(params, params + nparams);
+  c->pot.push_back(t);
+  return 0;
+}
+
+int qmc_add_estimator(qmc_ctx *c, int est_kind, const int *sets, int nsets, int bins, double minx, double maxx,
+                      const double *extra, int nextra, int *est_index)
+{
+  if (!c) return 1;
+  if (c->planned) return fail(c, "estimators must be added before qmc_set_dmc");
+  if (nsets < 1 || bins < 1) return fail(c, "estimator: sets/bins missing");
+  EstTerm t;
+  t.kind = est_kind;
+  t.sets.assign(sets, sets + nsets);
+  t.bins = bins;
+  t.minx = minx;
+  t.maxx = maxx;
+  if (extra && nextra > 0) t.extra.assign(extra, extra + nextra);
+  if (est_kind == QMC_EST_STRUCTUREFACTOR)
+    {
+      t.minx = 0;
+      t.maxx = bins;
+    }
+  if (est_index) *est_index = (int)c->est.size();
+  c->est.push_back(t);
+  return 0;
+}
+
+int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t deltaWalkers, uint64_t seed,
+                int branching_on, int64_t capacity)
+{
+  if (!c) return 1;
+  if (c->planned) return fail(c, "qmc_set_dmc called twice");
+  cudaSetDevice(c->device);
+  if (build_plan(c)) return 1;
+  DmcParams &D = c->dmc;
+  D.tau = timeStep;
+  D.sqrt_tau = std::sqrt(timeStep);
+  D.mean_walkers = (double)targetWalkers;
+  D.delta_walkers = (double)deltaWalkers;
+  /* branching.cpp:84-96 (size_t arithmetic on meanWalkers/deltaWalkers) */
+  D.log_up = 1. / timeStep * std::log(targetWalkers * 1. / (double)(targetWalkers + deltaWalkers));
+  D.log_down = (targetWalkers > deltaWalkers) ? 1. / timeStep * std::log(targetWalkers * 1. / (double)(targetWalkers - deltaWalkers)) : 0.0;
+  D.seed_lo = (uint32_t)seed;
+  D.seed_hi = (uint32_t)(seed >> 32);
+  D.branching_on = branching_on ? 1 : 0;
+  D.rank = c->rank;
+  D.nranks = c->nranks;
+  if (capacity <= 0) capacity = 2 * (targetWalkers + deltaWalkers) / std::max(1, c->nranks) + 64;
+  c->cap = capacity;
+  const size_t dofs = c->plan.dofs;
+  for (int b = 0; b < 2; ++b)
+    {
+      CK(cudaMalloc(&c->buf[b].R, capacity * dofs * 8));
+      CK(cudaMalloc(&c->buf[b].F, capacity * dofs * 8));
+      CK(cudaMalloc(&c->buf[b].logpsi, capacity * 8));
+      CK(cudaMalloc(&c->buf[b].E, capacity * 8));
+    }
+  CK(cudaMalloc(&c->parent, capacity * 4));
+  CK(cudaMalloc(&c->n_desc, capacity * 4));
+  c->cfg.grid = grid_for(c, capacity);
+  c->n_partials = c->cfg.grid * c->cfg.groups_per_cta;
+  CK(cudaMalloc(&c->partials, (size_t)c->n_partials * 2 * 8));
+  CK(cudaMemset(c->partials, 0, (size_t)c->n_partials * 2 * 8));
+  if (!c->coefpool.empty())
+    {
+      CK(cudaMalloc(&c->coef, c->coefpool.size() * 8));
+      CK(cudaMemcpy(c->coef, c->coefpool.data(), c->coefpool.size() * 8, cudaMemcpyHostToDevice));
+    }
+  if (c->plan.hist_stride > 0)
+    {
+      c->plan.hist_replicas = c->cfg.grid;
+      CK(cudaMalloc(&c->hist, (size_t)c->cfg.grid * c->plan.hist_stride * 8));
+      CK(cudaMemset(c->hist, 0, (size_t)c->cfg.grid * c->plan.hist_stride * 8));
+      CK(cudaMalloc(&c->hist_out, (size_t)c->plan.hist_stride * 8));
+    }
+  c->planned = true;
+  return 0;
+}
+
+static int eval_common(qmc_ctx *c, const double *dR, int64_t nW, double *dlogpsi, double *dgrad, double *dlap,
+                       double *dV, double *dE, int *dvalid, bool hist, int flag_invalid)
+{
+  EvalArgs a;
+  memset(&a, 0, sizeof a);
+  a.R = dR;
+  a.nW = (int)nW;
+  a.logpsi = dlogpsi;
+  a.F = dgrad;
+  a.lap = dlap;
+  a.V = dV;
+  a.E = dE;
+  a.valid = dvalid;
+  a.coef = c->coef;
+  a.hist = hist ? c->hist : nullptr;
+  a.ctl = c->ctl;
+  a.flag_invalid = flag_invalid;
+  LaunchCfg cfg = c->cfg;
+  cfg.grid = std::min(c->cfg.grid, grid_for(c, nW));
+  CK(launch_eval(c->ksel, hist, cfg, c->stream, c->plan, a));
+  c->launches += 1;
+  return 0;
+}
+
+int qmc_eval_device(qmc_ctx *c, const double *dR, int64_t nW, double *dlogpsi, double *dgrad, double *dlap, double *dV,
+                    double *dE, int *dvalid)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  cudaSetDevice(c->device);
+  if (nW <= 0) return 0;
+  return eval_common(c, dR, nW, dlogpsi, dgrad, dlap, dV, dE, dvalid, false, 0);
+}
+
+int qmc_eval(qmc_ctx *c, const double *R, int64_t nW, double *logpsi, double *grad, double *lap, double *V, double *E, int *valid)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  cudaSetDevice(c->device);
+  if (nW <= 0) return 0;
+  const size_t dofs = c->plan.dofs;
+  const size_t need = (size_t)nW * (2 * dofs + 4) * 8;
+  if (ensure_scratch(c, need, (size_t)nW * 4)) return 1;
+  double *dR = c->scr, *dF = dR + nW * dofs, *dlp = dF + nW * dofs, *dlap = dlp + nW, *dV = dlap + nW, *dE = dV + nW;
+  CK(cudaMemcpyAsync(dR, R, nW * dofs * 8, cudaMemcpyHostToDevice, c->stream));
+  if (eval_common(c, dR, nW, dlp, dF, dlap, dV, dE, c->scr_i, false, 0)) return 1;
+  if (logpsi) CK(cudaMemcpyAsync(logpsi, dlp, nW * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (grad) CK(cudaMemcpyAsync(grad, dF, nW * dofs * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (lap) CK(cudaMemcpyAsync(lap, dlap, nW * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (V) CK(cudaMemcpyAsync(V, dV, nW * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (E) CK(cudaMemcpyAsync(E, dE, nW * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (valid) CK(cudaMemcpyAsync(valid, c->scr_i, nW * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int qmc_accumulate_configs(qmc_ctx *c, const double *R, int64_t nW)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (!c->has_hist) return fail(c, "no estimators registered");
+  cudaSetDevice(c->device);
+  if (nW <= 0) return 0;
+  const size_t dofs = c->plan.dofs;
+  if (ensure_scratch(c, (size_t)nW * (dofs + 1) * 8, (size_t)nW * 4)) return 1;
+  CK(cudaMemcpyAsync(c->scr, R, nW * dofs * 8, cudaMemcpyHostToDevice, c->stream));
+  if (eval_common(c, c->scr, nW, nullptr, nullptr, nullptr, nullptr, nullptr, c->scr_i, true, 0)) return 1;
+  std::vector<int> valid(nW);
+  CK(cudaMemcpyAsync(valid.data(), c->scr_i, nW * 4, cudaMemcpyDeviceToHost, c->stream));
+  Ctl h;
+  CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  double w = 0;
+  for (int v : valid) w += v ? 1 : 0;
+  h.est_weight += w;
+  CK(cudaMemcpy(&c->ctl->est_weight, &h.est_weight, 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int qmc_upload_walkers(qmc_ctx *c, const double *R, int64_t nW)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  cudaSetDevice(c->device);
+  if (nW < 1) return fail(c, "need at least one walker");
+  if (nW > c->cap) return fail(c, "more walkers than capacity");
+  const size_t dofs = c->plan.dofs;
+  WalkerBuf &B = c->buf[c->cur];
+  CK(cudaMemcpyAsync(B.R, R, nW * dofs * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(&c->ctl->invalid_init, 0, 4, c->stream));
+  if (eval_common(c, B.R, nW, B.logpsi, B.F, nullptr, nullptr, B.E, nullptr, false, 1)) return 1;
+  CK(launch_init_identity(c->stream, c->parent, c->n_desc, (int)nW, c->ctl));
+  // first E_T: brancher->setEnergyShift(current_walkers) (dmcDriver.cpp:191)
+  StepArgs a = make_step_args(c, 0);
+  a.out = B;
+  CK(launch_scan(c->stream, c->dmc, a, 0, c->nranks > 1, 1));
+  c->launches += 2;
+  if (allreduce_sums(c)) return 1;
+  Ctl h;
+  CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (h.invalid_init) return fail(c, "Inalid initial configurations.");   /* dmcDriver.cpp:166-170 (sic) */
+  return 0;
+}
+
+int qmc_download_walkers(qmc_ctx *c, double *R, int64_t capW, int64_t *nW, double *E)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  cudaSetDevice(c->device);
+  Ctl h;
+  CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int64_t n = h.n_cur;
+  if (nW) *nW = n;
+  if (!R || n == 0) return 0;
+  if (n > capW) return fail(c, "download buffer too small");
+  const size_t dofs = c->plan.dofs;
+  if (ensure_scratch(c, (size_t)n * (dofs + 1) * 8, 0)) return 1;
+  gather_kernel<<<(int)n, 128, 0, c->stream>>>(c->buf[c->cur], c->parent, (int)dofs, (int)n, c->scr, c->scr + n * dofs);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(R, c->scr, n * dofs * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (E) CK(cudaMemcpyAsync(E, c->scr + n * dofs, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int qmc_step(qmc_ctx *c, int nSteps, int sampleEvery)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  cudaSetDevice(c->device);
+  if (sampleEvery < 1) sampleEvery = 1;
+  CK(cudaEventRecord(c->ev0, c->stream));
+  for (int k = 0; k < nSteps; ++k)
+    {
+      c->sample_phase += 1;
+      const int accumulate = (c->sample_phase % sampleEvery) == 0;
+      if (one_step(c, accumulate, nullptr)) return 1;
+    }
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->device_ms += ms;
+  return 0;
+}
+
+int qmc_step_traced(qmc_ctx *c, int accumulate, const qmc_trace *tr, int64_t traceCap, int64_t *nW_before, int64_t *nW_after)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  cudaSetDevice(c->device);
+  Ctl h;
+  CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int64_t n = h.n_cur;
+  if (nW_before) *nW_before = n;
+  if (tr && n > traceCap) return fail(c, "trace buffers too small");
+  const size_t dofs = c->plan.dofs;
+  TraceDev T;
+  memset(&T, 0, sizeof T);
+  double *dbuf = nullptr;
+  int *ibuf = nullptr;
+  if (tr)
+    {
+      CK(cudaMalloc(&dbuf, (size_t)n * (3 * dofs + 7) * 8));
+      CK(cudaMalloc(&ibuf, (size_t)n * 4 * 4));
+      T.xi = dbuf;
+      T.Rprop = T.xi + n * dofs;
+      T.Fprop = T.Rprop + n * dofs;
+      T.logpsi = T.Fprop + n * dofs;
+      T.lap = T.logpsi + n;
+      T.V = T.lap + n;
+      T.Eprop = T.V + n;
+      T.q = T.Eprop + n;
+      T.u_m = T.q + n;
+      T.u_b = T.u_m + n;
+      T.accepted = ibuf;
+      T.valid = ibuf + n;
+      T.n_desc = ibuf + 2 * n;
+      T.parent = ibuf + 3 * n;
+    }
+  int rc = one_step(c, accumulate, tr ? &T : nullptr);
+  if (!rc && tr)
+    {
+      auto D = [&](void *dst, const void *src, size_t bytes) {
+        if (dst) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+      };
+      D(tr->xi, T.xi, n * dofs * 8);
+      D(tr->Rprop, T.Rprop, n * dofs * 8);
+      D(tr->Fprop, T.Fprop, n * dofs * 8);
+      D(tr->logpsi, T.logpsi, n * 8);
+      D(tr->lap, T.lap, n * 8);
+      D(tr->V, T.V, n * 8);
+      D(tr->Eprop, T.Eprop, n * 8);
+      D(tr->q, T.q, n * 8);
+      D(tr->u_metropolis, T.u_m, n * 8);
+      D(tr->u_branch, T.u_b, n * 8);
+      D(tr->accepted, T.accepted, n * 4);
+      D(tr->valid, T.valid, n * 4);
+      D(tr->n_desc, T.n_desc, n * 4);
+      D(tr->parent, T.parent, n * 4);
+    }
+  cudaStreamSynchronize(c->stream);
+  if (dbuf) cudaFree(dbuf);
+  if (ibuf) cudaFree(ibuf);
+  if (rc) return rc;
+  CK(cudaMemcpy(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost));
+  if (nW_after) *nW_after = h.n_cur;
+  return 0;
+}
+
+int qmc_block_results(qmc_ctx *c, qmc_block_result *out)
+{
+  if (!c || !out) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  cudaSetDevice(c->device);
+  Ctl h;
+  CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  double v[4] = {h.blk_esum, h.blk_ecount, h.blk_moves, h.blk_acc};
+  if (c->nranks > 1)
+    {
+      if (ensure_scratch(c, 64, 0)) return 1;
+      CK(cudaMemcpyAsync(c->scr, v, 32, cudaMemcpyHostToDevice, c->stream));
+      NK(g_nccl.AllReduce(c->scr, c->scr, 4, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+      CK(cudaMemcpyAsync(v, c->scr, 32, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+  out->energy_sum = v[0];
+  out->energy_count = v[1];
+  out->n_moves = v[2];
+  out->n_accepted = v[3];
+  out->population = h.n_cur;
+  out->energy_shift = h.eshift;
+  out->steps_done = h.blk_steps;
+  out->overflow = h.overflow;
+  out->device_ms = c->device_ms;
+  c->device_ms = 0;
+  CK(cudaMemsetAsync(&c->ctl->blk_esum, 0, 5 * 8, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int qmc_get_estimator(qmc_ctx *c, int est_index, double *sums, int bins, double *weight)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (est_index < 0 || est_index >= c->plan.nest) return fail(c, "estimator index out of range");
+  const Estimator &E = c->plan.est[est_index];
+  if (bins != E.bins) return fail(c, "bins mismatch");
+  cudaSetDevice(c->device);
+  CK(launch_reduce_hist(c->stream, c->hist, c->plan.hist_replicas, c->plan.hist_stride, c->hist_out));
+  c->launches += 1;
+  Ctl h;
+  CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  double w = 0;
+  if (c->nranks > 1)
+    {
+      NK(g_nccl.AllReduce(c->hist_out, c->hist_out, c->plan.hist_stride, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+      if (ensure_scratch(c, 64, 0)) return 1;
+      CK(cudaStreamSynchronize(c->stream));
+      w = h.est_weight;
+      CK(cudaMemcpyAsync(c->scr, &w, 8, cudaMemcpyHostToDevice, c->stream));
+      NK(g_nccl.AllReduce(c->scr, c->scr, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+      CK(cudaMemcpyAsync(&w, c->scr, 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+  CK(cudaMemcpyAsync(sums, c->hist_out + E.offset, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->nranks == 1) w = h.est_weight;
+  if (weight) *weight = w;
+  return 0;
+}
+
+int qmc_clear_estimators(qmc_ctx *c)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  cudaSetDevice(c->device);
+  if (c->hist) CK(cudaMemsetAsync(c->hist, 0, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8, c->stream));
+  CK(cudaMemsetAsync(&c->ctl->est_weight, 0, 8, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int qmc_synchronize(qmc_ctx *c)
+{
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------
+int qmc_comm_unique_id(void *uniqueId128)
+{
+  std::string err;
+  if (!g_nccl.load(err))
+    {
+      g_create_error = err;
+      return 1;
+    }
+  ncclUniqueId_t id;
+  int e = g_nccl.GetUniqueId(&id);
+  if (e)
+    {
+      g_create_error = g_nccl.GetErrorString(e);
+      return 1;
+    }
+  memcpy(uniqueId128, &id, 128);
+  return 0;
+}
+
+int qmc_comm_init(qmc_ctx *c, const void *uniqueId128, int rank, int nranks)
+{
+  if (!c) return 1;
+  if (c->planned) return fail(c, "qmc_comm_init must precede qmc_set_dmc");
+  if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return fail(c, "invalid rank/nranks (max 8 ranks)");
+  cudaSetDevice(c->device);
+  c->rank = rank;
+  c->nranks = nranks;
+  if (nranks == 1) return 0;
+  if (!g_nccl.load(c->err)) return 1;
+  ncclUniqueId_t id;
+  memcpy(&id, uniqueId128, 128);
+  NK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+  return 0;
+}
+
+int qmc_plan_rebalance(const int *populations, int nRanks, int *sources, int *amounts)
+{
+  /* Alias-method planner with the semantics of determineLoadBalanceComunicationsAliasMethod
+     (dmc/ptools.cpp:93-161): ranks are partitioned into <=k and >k (k = floor(W/P), the first
+     r = W mod P positions of the partitioned order get k+1); every under-full rank receives its
+     whole deficit from the current over-full rank. */
+  if (nRanks < 1) return 1;
+  std::vector<int> pop(populations, populations + nRanks), perm(nRanks);
+  for (int i = 0; i < nRanks; ++i)
+    {
+      perm[i] = i;
+      sources[i] = 0;
+      amounts[i] = 0;
+    }
+  long total = 0;
+  for (int p : pop) total += p;
+  const int k = (int)(total / nRanks), r = (int)(total % nRanks);
+  int i = 0;
+  while (i < nRanks && pop[i] <= k) ++i;
+  for (int j = i + 1; j < nRanks; ++j)
+    if (pop[j] <= k)
+      {
+        std::swap(pop[i], pop[j]);
+        std::swap(perm[i], perm[j]);
+        ++i;
+      }
+  auto balanced = [&](int idx) { return k + (idx < r ? 1 : 0); };
+  int j = 0;
+  while (i > j && i < nRanks)
+    {
+      const int J = perm[j], I = perm[i];
+      sources[J] = I;
+      amounts[J] = balanced(j) - pop[j];
+      pop[i] -= amounts[J];
+      if (pop[i] < balanced(i)) ++i;
+      ++j;
+    }
+  return 0;
+}
+
+int qmc_rebalance(qmc_ctx *c, int64_t *moved)
+{
+  if (!c) return 1;
+  if (moved) *moved = 0;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->nranks == 1) return 0;
+  cudaSetDevice(c->device);
+  Ctl h;
+  CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  // populations of every rank: the one-hot vector carried by the per-step all-reduce
+  std::vector<int> pops(c->nranks), src(c->nranks), amt(c->nranks);
+  for (int r = 0; r < c->nranks; ++r) pops[r] = (int)h.gsum[2 + r];
+  if (pops[c->rank] != h.n_cur) return fail(c, "population vector out of date");
+  qmc_plan_rebalance(pops.data(), c->nranks, src.data(), amt.data());
+  const size_t dofs = c->plan.dofs, wsz = 2 * dofs + 2;
+  int n_send = 0;
+  for (int r = 0; r < c->nranks; ++r)
+    if (amt[r] > 0 && src[r] == c->rank) n_send += amt[r];
+  const int n_recv = amt[c->rank];
+  const size_t need = (size_t)std::max(n_send, n_recv) * wsz * 8;
+  if (need > c->slab_bytes)
+    {
+      cudaFree(c->slab_send);
+      cudaFree(c->slab_recv);
+      c->slab_send = c->slab_recv = nullptr;
+      CK(cudaMalloc(&c->slab_send, need));
+      CK(cudaMalloc(&c->slab_recv, need));
+      c->slab_bytes = need;
+    }
+  int n_cur = h.n_cur;
+  if (n_recv > 0 && h.n_prev + n_recv > c->cap) return fail(c, "rebalance: capacity exceeded");
+  // senders ship their TAIL walkers (ptools.cpp:297-303)
+  if (n_send > 0) CK(launch_pack(c->stream, c->buf[c->cur], c->parent, (int)dofs, n_cur - n_send, n_send, c->slab_send));
+  NK(g_nccl.GroupStart());
+  {
+    size_t off = 0;
+    for (int r = 0; r < c->nranks; ++r)
+      if (amt[r] > 0 && src[r] == c->rank)
+        {
+          NK(g_nccl.Send(c->slab_send + off, (size_t)amt[r] * wsz, NCCL_FLOAT64, r, c->comm, c->stream));
+          off += (size_t)amt[r] * wsz;
+        }
+    if (n_recv > 0) NK(g_nccl.Recv(c->slab_recv, (size_t)n_recv * wsz, NCCL_FLOAT64, src[c->rank], c->comm, c->stream));
+  }
+  NK(g_nccl.GroupEnd());
+  n_cur -= n_send;
+  if (n_recv > 0)
+    { // received walkers land in free physical slots [n_prev, n_prev+n_recv) and are appended to the population
+      CK(launch_unpack(c->stream, c->buf[c->cur], (int)dofs, h.n_prev, n_recv, c->slab_recv));
+      std::vector<int> par(n_recv);
+      for (int i = 0; i < n_recv; ++i) par[i] = h.n_prev + i;
+      CK(cudaMemcpyAsync(c->parent + n_cur, par.data(), (size_t)n_recv * 4, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      n_cur += n_recv;
+    }
+  int np = h.n_prev + n_recv;
+  CK(cudaMemcpyAsync(&c->ctl->n_cur, &n_cur, 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(&c->ctl->n_prev, &np, 4, cudaMemcpyHostToDevice, c->stream));
+  double newpop = n_cur;
+  CK(cudaMemcpyAsync(&c->ctl->gsum[2 + c->rank], &newpop, 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->launches += 2;
+  if (moved) *moved = (int64_t)n_send - n_recv;
+  return 0;
+}
+
+int qmc_get_info(qmc_ctx *c, const char *key, double *value)
+{
+  if (!c || !key || !value) return 1;
+  const std::string k = key;
+  if (k == "dofs") *value = c->plan.dofs;
+  else if (k == "capacity") *value = (double)c->cap;
+  else if (k == "grid") *value = c->cfg.grid;
+  else if (k == "block") *value = c->cfg.block;
+  else if (k == "smem_bytes") *value = (double)c->cfg.smem;
+  else if (k == "warps_per_walker") *value = c->cfg.nwarps_per_group;
+  else if (k == "kernel_variant") *value = c->ksel;
+  else if (k == "launches") *value = (double)c->launches;
+  else if (k == "sms") *value = c->sms;
+  else if (k == "regs_propagate") *value = propagate_regs(c->ksel, false);
+  else if (k == "regs_eval") *value = eval_regs(c->ksel, false);
+  else if (k == "n_pair_passes") *value = c->plan.n2b;
+  else if (k == "fp64_peak_tflops")
+    {
+      cudaSetDevice(c->device);
+      *value = measure_fp64_peak_tflops(c->stream, nullptr);
+    }
+  else return fail(c, "unknown info key " + k);
+  return 0;
+}
+
+void *qmc_stream(qmc_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+} // extern "C"

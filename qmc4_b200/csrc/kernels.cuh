@@ -1,0 +1,87 @@
+// kernels.cuh — device-side state and the launch interface between capi.cu and the kernels.
+#pragma once
+#include "plan.h"
+#include <cuda_runtime.h>
+
+namespace qmc {
+
+// One walker buffer (HBM, SoA over walkers; each walker's dofs doubles are contiguous in the
+// reference's own per-walker layout so a group streams them with coalesced loads).
+struct WalkerBuf {
+  double *R;        // [cap*dofs]
+  double *F;        // [cap*dofs]  grad log psi
+  double *logpsi;   // [cap]
+  double *E;        // [cap]       local energy of the configuration
+};
+
+constexpr int MAX_RANKS = 8;
+
+// Device-resident control block: everything the step sequence needs lives here so that
+// qmc_step() enqueues kernels without ever reading back (population, E_T, counters).
+struct Ctl {
+  int n_cur;                   // walkers in the current population (input of the next propagate)
+  int overflow;                // population exceeded capacity
+  int invalid_init;            // a constraint was violated during initial evaluation
+  int n_prev;                  // physical slots [0,n_prev) of the current buffer are referenced by the parent map
+  unsigned long long step;     // global step counter (Philox counter word)
+  double eshift;               // E_T in use  (branching.cpp:65-97)
+  double lsum[2 + MAX_RANKS];  // local  {sum E, population, one-hot population vector}
+  double gsum[2 + MAX_RANKS];  // global {sum E, population, populations per rank} (after all-reduce)
+  double blk_esum, blk_ecount; // energy estimator (scalarAccumulator, accumulators.h:21-47)
+  double blk_moves, blk_acc;   // metropolis counters (metropolis.cpp:24-26)
+  double blk_steps;
+  double est_weight;           // walkers accumulated into the histogram estimators
+};
+
+struct TraceDev {              // optional per-walker trace (device pointers, may be null)
+  double *xi, *Rprop, *Fprop, *logpsi, *lap, *V, *Eprop, *q, *u_m, *u_b;
+  int *accepted, *valid, *n_desc, *parent;
+};
+
+struct StepArgs {
+  WalkerBuf in, out;
+  int *parent;                 // [cap] source slot in `in` for each slot of `out` (rewritten by the scan)
+  int *n_desc;                 // [cap]
+  double *partials;            // [grid*groups*2] moves / accepted per group
+  Ctl *ctl;
+  const double *coef;          // spline coefficient pool
+  double *hist;                // histogram replicas [grid][hist_stride] or null
+  int accumulate;              // sampling step: estimators on
+  int cap;
+  TraceDev trace;
+};
+
+struct EvalArgs {
+  const double *R;             // [nW*dofs]
+  int nW;
+  double *logpsi, *F, *lap, *V, *E;   // any may be null
+  int *valid;
+  const double *coef;
+  double *hist;                // replicas or null
+  Ctl *ctl;
+  int flag_invalid;            // set ctl->invalid_init when a configuration is invalid
+};
+
+struct LaunchCfg {
+  int grid, block, nwarps_per_group, groups_per_cta;
+  size_t smem;
+};
+
+// kernel selectors
+enum : int { KSEL_GG_STEP = 0, KSEL_GG_NONE = 1, KSEL_GAUSS_NONE = 2, KSEL_GENERIC = 3, KSEL_COUNT = 4 };
+
+cudaError_t launch_eval(int ksel, bool hist, const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const EvalArgs &a);
+cudaError_t launch_propagate(int ksel, bool hist, const LaunchCfg &cfg, cudaStream_t st, const Plan &plan,
+                             const DmcParams &dmc, const StepArgs &a);
+cudaError_t launch_scan(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, int n_partials, int multi_rank, int init_mode);
+cudaError_t launch_finalize_shift(cudaStream_t st, const DmcParams &dmc, Ctl *ctl);
+cudaError_t launch_init_identity(cudaStream_t st, int *parent, int *n_desc, int n, Ctl *ctl);
+cudaError_t launch_reduce_hist(cudaStream_t st, const double *hist, int replicas, int stride, double *out);
+cudaError_t launch_pack(cudaStream_t st, const WalkerBuf &buf, const int *parent, int dofs, int first, int count, double *slab);
+cudaError_t launch_unpack(cudaStream_t st, const WalkerBuf &buf, int dofs, int first, int count, const double *slab);
+cudaError_t configure_kernels(int max_smem_optin);
+int propagate_regs(int ksel, bool hist);
+int eval_regs(int ksel, bool hist);
+double measure_fp64_peak_tflops(cudaStream_t st, float *ms_out);
+
+} // namespace qmc
