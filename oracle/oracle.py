@@ -130,8 +130,177 @@ class Ref(_Base):
         super().__init__(REF_LIB, "ref")
 
 
+class _Model(C.Structure):
+    _fields_ = [("lBox", C.c_double * 3), ("nSpecies", C.c_int), ("N", C.POINTER(C.c_int)), ("nTerms", C.c_int),
+                ("ti", C.POINTER(C.c_int)), ("tp", C.POINTER(C.c_double))]
+
+
+_J = {"gaussian": (1, ("alpha",)), "gaussiangaussian": (2, ("r0", "u0")),
+      "squareWell": (3, ("V0", "R0", "Rm", "alpha", "aInverse", "cut_off")), "hardSphereGauss": (4, ("a", "Rm", "D")),
+      "bSpline": (5, ("stepSize", "valueRight", "derivativeRight")), "poschTeller": (6, ("R0", "C", "alpha", "Rm", "cut_off")),
+      "hardSphere": (7, ("a", "k", "cut_off")),
+      "squareWellBoundState": (8, ("V0", "R0", "Rm", "cut_off", "aInverse", "eb", "alpha"))}
+_WF = {"jastrow1b": 1, "jastrow2bUnDis": 2, "jastrow2bDis": 3, "jastrow3bUnDis": 4}
+_POT = {"harmonic1b": 1, "squareWell2b": 2, "dipolar2b": 3, "poschTeller2b": 4, "potentialTwoBody/squareWell": 5,
+        "potentialTwoBody/potentialBarrier": 6, "potentialThreeBodyUnDis/squareWell": 7,
+        "potentialThreeBodyUnDis/potentialBarrier": 8}
+_EST = {"pairCorrelation": 1, "trimerCorrelationUnDis": 2, "structureFactor": 3}
+
+
+def flatten(cfg):
+    """input.json (dict) -> flat term list of qmc_oracle.h, in the reference's term order."""
+    ti, tp = [], []
+
+    def add(cls, kind, sets, jk, params):
+        sets = (list(sets) + [0, 0, 0])[:3]
+        ti.extend([cls, kind] + sets + [jk, len(params), len(tp)])
+        tp.extend(float(x) for x in params)
+
+    for w in cfg.get("wavefunctions", []):
+        jname = w["jastrow"]["kind"]
+        jk, keys = _J[jname]
+        params = [w["jastrow"][k] for k in keys]
+        if jname == "bSpline":
+            params += list(w["jastrow"]["coefficients"])
+        kind = _WF[w["kind"]]
+        sets = [w["set"]] if w["kind"] == "jastrow1b" else w["sets"]
+        if kind == 4:
+            params.append(w.get("hardSphereRadius", -1.0))
+        add(1, kind, sets, jk, params)
+    for p in cfg.get("potentials", []):
+        name = p["kind"] + ("/" + p["functor"]["kind"] if "functor" in p else "")
+        kind = _POT[name]
+        if kind == 1:
+            add(2, kind, [p["set"]], 0, [p["omega"]])
+        elif kind == 2:
+            add(2, kind, p["sets"], 0, [p["V0"], p["R0"]])
+        elif kind == 3:
+            add(2, kind, p["sets"], 0, [p["D"]])
+        elif kind == 4:
+            add(2, kind, p["sets"], 0, [p["R0"]])
+        else:
+            add(2, kind, p["sets"], 0, [p["functor"]["R0"], p["functor"]["V0"]])
+    for e in cfg.get("measurements", []):
+        if e["kind"] in ("energy", "forceEnergy"):
+            continue
+        kind = _EST[e["kind"]]
+        if kind == 3:
+            add(3, kind, e["sets"], e["bins"], [e["maxq"], e["lBox"], e["channel"]])
+        else:
+            add(3, kind, e["sets"], e["bins"], [e["minx"], e["maxx"]])
+    return np.asarray(ti, dtype=np.int32), np.asarray(tp if tp else [0.0], dtype=np.float64)
+
+
 class Port(_Base):
+    """Plain-C restatement (oracle/qmc_oracle.c)."""
+
     def __init__(self):
         if not have_port():
             raise FileNotFoundError(PORT_LIB + " — run `make -C oracle port`")
         super().__init__(PORT_LIB, "orc")
+        self.lib.orc_energy_shift.restype = C.c_double
+        self.lib.orc_energy_shift.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double, C.c_double]
+        self.lib.orc_n_descendants.argtypes = [C.c_double] * 5
+
+    def _model(self, cfg):
+        ti, tp = flatten(cfg)
+        N = np.asarray(cfg["N"], dtype=np.int32)
+        m = _Model()
+        for d in range(3):
+            m.lBox[d] = cfg["lBox"][d]
+        m.nSpecies = len(N)
+        m.N = _ip(N)
+        m.nTerms = len(ti) // 8
+        m.ti = _ip(ti)
+        m.tp = _dp(tp)
+        m._keep = (ti, tp, N)
+        return m
+
+    def eval(self, cfg, R):
+        m = self._model(cfg)
+        d = _dofs(cfg)
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, d)
+        nW = R.shape[0]
+        out = dict(logpsi=np.zeros(nW), grad=np.zeros((nW, d)), lap=np.zeros(nW), V=np.zeros(nW), E=np.zeros(nW),
+                   valid=np.zeros(nW, dtype=np.int32))
+        self._ck(self.lib.orc_eval_model(C.byref(m), _dp(R), nW, _dp(out["logpsi"]), _dp(out["grad"]), _dp(out["lap"]),
+                                         _dp(out["V"]), _dp(out["E"]), _ip(out["valid"])))
+        return out
+
+    def green_ratio(self, cfg, tau, Rnew, Fnew, Rold, Fold):
+        m = self._model(cfg)
+        d = _dofs(cfg)
+        a = [np.ascontiguousarray(x, dtype=np.float64).reshape(-1, d) for x in (Rnew, Fnew, Rold, Fold)]
+        q = np.zeros(a[0].shape[0])
+        self._ck(self.lib.orc_green_ratio_model(C.byref(m), C.c_double(tau), len(q), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(q)))
+        return q
+
+    @staticmethod
+    def draw_order(cfg, xi_layout):
+        d = _dofs(cfg)
+        xi_layout = np.asarray(xi_layout, dtype=np.float64).reshape(-1, d)
+        nW = xi_layout.shape[0]
+        xi = np.zeros_like(xi_layout)
+        off = 0
+        for n in cfg["N"]:
+            blk = xi_layout[:, off:off + 3 * n].reshape(nW, 3, n)
+            xi[:, off:off + 3 * n] = blk.transpose(0, 2, 1).reshape(nW, 3 * n)
+            off += 3 * n
+        return np.ascontiguousarray(xi)
+
+    def drift_diffuse(self, cfg, tau, Rold, Fold, xi_layout):
+        m = self._model(cfg)
+        d = _dofs(cfg)
+        Rold = np.ascontiguousarray(Rold, dtype=np.float64).reshape(-1, d)
+        Fold = np.ascontiguousarray(Fold, dtype=np.float64).reshape(-1, d)
+        xi = self.draw_order(cfg, xi_layout)
+        out = np.zeros_like(Rold)
+        self._ck(self.lib.orc_drift_diffuse_model(C.byref(m), C.c_double(tau), Rold.shape[0], _dp(Rold), _dp(Fold), _dp(xi), _dp(out)))
+        return out
+
+    def update(self, cfg, tau, Rold, xi_layout, u_m):
+        """dmcDriver::update for every walker given the random numbers it consumes."""
+        m = self._model(cfg)
+        d = _dofs(cfg)
+        Rold = np.ascontiguousarray(Rold, dtype=np.float64).reshape(-1, d)
+        nW = Rold.shape[0]
+        xi = self.draw_order(cfg, xi_layout)
+        u_m = np.ascontiguousarray(u_m, dtype=np.float64)
+        out = dict(R=np.zeros((nW, d)), F=np.zeros((nW, d)), logpsi=np.zeros(nW), E=np.zeros(nW), accepted=np.zeros(nW, dtype=np.int32))
+        self._ck(self.lib.orc_update_model(C.byref(m), C.c_double(tau), nW, _dp(Rold), _dp(xi), _dp(u_m), _dp(out["R"]), _dp(out["F"]),
+                                           _dp(out["logpsi"]), _dp(out["E"]), _ip(out["accepted"])))
+        return out
+
+    def histogram(self, cfg, R, iMeas, bins):
+        m = self._model(cfg)
+        d = _dofs(cfg)
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, d)
+        sums = np.zeros(bins)
+        w = C.c_double(0)
+        self._ck(self.lib.orc_histogram_model(C.byref(m), _dp(R), R.shape[0], iMeas, _dp(sums), bins, C.byref(w)))
+        return sums, w.value
+
+    def plan(self, populations):
+        p = np.asarray(populations, dtype=np.int32)
+        src = np.zeros(len(p), dtype=np.int32)
+        amt = np.zeros(len(p), dtype=np.int32)
+        self._ck(self.lib.orc_plan(_ip(p), len(p), _ip(src), _ip(amt)))
+        return src, amt
+
+    def energy_shift(self, E, tau, mean, delta):
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        return self.lib.orc_energy_shift(_dp(E), len(E), tau, mean, delta)
+
+    def n_descendants(self, Enew, Eold, eT, tau, u):
+        return np.asarray([self.lib.orc_n_descendants(float(a), float(b), float(eT), float(tau), float(c))
+                           for a, b, c in zip(Enew, Eold, u)], dtype=np.int32)
+
+    def branch(self, nDesc, E):
+        nDesc = np.ascontiguousarray(nDesc, dtype=np.int32)
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        cap = int(max(nDesc.sum(), len(E))) + 8
+        out = np.zeros(cap)
+        n = self.lib.orc_branch(_ip(nDesc), _dp(E), len(E), _dp(out), cap)
+        if n < 0:
+            raise RuntimeError("orc_branch: capacity")
+        return out[:n]

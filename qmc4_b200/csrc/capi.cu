@@ -119,6 +119,13 @@ struct qmc_ctx {
   double *slab_send = nullptr, *slab_recv = nullptr;
   size_t slab_bytes = 0;
   long launches = 0;
+  // per-launch timing of the dominant kernel (propagate): ring of event pairs resolved at sync points
+  static constexpr int NEV = 256;
+  cudaEvent_t pev0[NEV] = {}, pev1[NEV] = {};
+  int pev_used = 0;
+  double prop_ms = 0;
+  long prop_launches_timed = 0;
+  int time_kernels = 0;
 };
 
 namespace {
@@ -580,6 +587,19 @@ int allreduce_sums(qmc_ctx *c)
   return 0;
 }
 
+int resolve_kernel_timers(qmc_ctx *c)
+{ // call after a stream synchronisation
+  for (int i = 0; i < c->pev_used; ++i)
+    {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, c->pev0[i], c->pev1[i]));
+      c->prop_ms += ms;
+      c->prop_launches_timed += 1;
+    }
+  c->pev_used = 0;
+  return 0;
+}
+
 StepArgs make_step_args(qmc_ctx *c, int accumulate)
 {
   StepArgs a;
@@ -602,7 +622,10 @@ int one_step(qmc_ctx *c, int accumulate, const TraceDev *tr)
   StepArgs a = make_step_args(c, accumulate);
   if (tr) a.trace = *tr;
   const bool hist = accumulate && c->has_hist;
+  const bool timed = c->time_kernels && c->pev_used < qmc_ctx::NEV;
+  if (timed) CK(cudaEventRecord(c->pev0[c->pev_used], c->stream));
   CK(launch_propagate(c->ksel, hist, c->cfg, c->stream, c->plan, c->dmc, a));
+  if (timed) CK(cudaEventRecord(c->pev1[c->pev_used++], c->stream));
   CK(launch_scan(c->stream, c->dmc, a, c->n_partials, c->nranks > 1, 0));
   c->launches += 2;
   c->cur ^= 1;
@@ -667,6 +690,11 @@ int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, co
   if ((e = configure_kernels(c->max_smem)) != cudaSuccess) return bail(std::string("kernel image: ") + cudaGetErrorString(e));
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  for (int i = 0; i < qmc_ctx::NEV; ++i)
+    {
+      cudaEventCreate(&c->pev0[i]);
+      cudaEventCreate(&c->pev1[i]);
+    }
   if ((e = cudaMalloc(&c->ctl, sizeof(Ctl))) != cudaSuccess) return bail(cudaGetErrorString(e));
   cudaMemset(c->ctl, 0, sizeof(Ctl));
   memset(&c->dmc, 0, sizeof c->dmc);
@@ -699,6 +727,11 @@ void qmc_destroy(qmc_ctx *c)
   cudaFree(c->slab_send);
   cudaFree(c->slab_recv);
   if (c->comm) g_nccl.CommDestroy(c->comm);
+  for (int i = 0; i < qmc_ctx::NEV; ++i)
+    {
+      if (c->pev0[i]) cudaEventDestroy(c->pev0[i]);
+      if (c->pev1[i]) cudaEventDestroy(c->pev1[i]);
+    }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -955,7 +988,7 @@ int qmc_step(qmc_ctx *c, int nSteps, int sampleEvery)
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->device_ms += ms;
-  return 0;
+  return resolve_kernel_timers(c);
 }
 
 int qmc_step_traced(qmc_ctx *c, int accumulate, const qmc_trace *tr, int64_t traceCap, int64_t *nW_before, int64_t *nW_after)
@@ -1263,6 +1296,11 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "regs_propagate") *value = propagate_regs(c->ksel, false);
   else if (k == "regs_eval") *value = eval_regs(c->ksel, false);
   else if (k == "n_pair_passes") *value = c->plan.n2b;
+  else if (k == "time_kernels_on") { c->time_kernels = 1; *value = 1; }
+  else if (k == "time_kernels_off") { c->time_kernels = 0; *value = 0; }
+  else if (k == "propagate_ms_total") *value = c->prop_ms;
+  else if (k == "propagate_launches_timed") *value = (double)c->prop_launches_timed;
+  else if (k == "propagate_timers_reset") { c->prop_ms = 0; c->prop_launches_timed = 0; *value = 0; }
   else if (k == "fp64_peak_tflops")
     {
       cudaSetDevice(c->device);

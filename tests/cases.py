@@ -1,0 +1,105 @@
+"""Shared parity cases: the reference's input.json documents + seeded walker sets.
+
+Sizes are small enough for the CPU oracle to finish in seconds.  The same dictionaries are fed,
+unchanged, to the reference (oracle/_ref), the C restatement (oracle/qmc_oracle.c) and the CUDA
+product (through the C ABI)."""
+import numpy as np
+
+GG = {"kind": "gaussiangaussian", "r0": 1.0, "u0": -0.5}
+
+
+def pbc(N, L, jastrow=GG, pot="potentialBarrier", meas=None, walkers=64, **kw):
+    c = {"N": [N], "lBox": [L, L, L], "method": "dmc", "timeStep": 1e-3, "walkers": walkers, "seed": 7,
+         "stepsPerBlock": 10, "nBlocks": 1, "correlationSteps": 0,
+         "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": jastrow}],
+         "potentials": [] if pot is None else [{"kind": "potentialTwoBody", "sets": [0, 0], "functor": {"kind": pot, "R0": 1.0, "V0": 2.0}}],
+         "measurements": meas or []}
+    c.update(kw)
+    return c
+
+
+def trap(N=10, walkers=100):
+    return {"N": [N], "lBox": [1e4, 1e4, 1e4], "method": "dmc", "timeStep": 1e-3, "walkers": walkers, "seed": 1235,
+            "stepsPerBlock": 10, "nBlocks": 1, "correlationSteps": 0,
+            "wavefunctions": [{"kind": "jastrow1b", "set": 0, "jastrow": {"kind": "gaussian", "alpha": 0.5}},
+                              {"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": {"kind": "gaussian", "alpha": 0.05}}],
+            "potentials": [{"kind": "harmonic1b", "omega": 1.0, "set": 0}], "measurements": []}
+
+
+def three_body(N=16, L=5.0, hs=None, meas=True):
+    w3 = {"kind": "jastrow3bUnDis", "sets": [0], "jastrow": {"kind": "gaussiangaussian", "r0": 1.5, "u0": -0.2}}
+    if hs is not None:
+        w3["hardSphereRadius"] = hs
+    return {"N": [N], "lBox": [L] * 3, "method": "dmc", "timeStep": 1e-3, "walkers": 32, "seed": 5,
+            "stepsPerBlock": 10, "nBlocks": 1, "correlationSteps": 0,
+            "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": GG}, w3],
+            "potentials": [{"kind": "potentialThreeBodyUnDis", "sets": [0, 0, 0], "functor": {"kind": "squareWell", "R0": 1.5, "V0": 1.0}}],
+            "measurements": [{"kind": "trimerCorrelationUnDis", "label": "trimer", "sets": [0], "bins": 50, "minx": 0, "maxx": L / 2}] if meas else []}
+
+
+def mixture():
+    return {"N": [12, 20], "lBox": [5.0, 5.0, 5.0], "method": "dmc", "timeStep": 1e-3, "walkers": 16, "seed": 3,
+            "stepsPerBlock": 10, "nBlocks": 1, "correlationSteps": 0,
+            "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": GG},
+                              {"kind": "jastrow2bUnDis", "sets": [1, 1], "jastrow": {"kind": "gaussiangaussian", "r0": 0.8, "u0": -0.3}},
+                              {"kind": "jastrow2bDis", "sets": [0, 1], "jastrow": {"kind": "gaussiangaussian", "r0": 1.2, "u0": 0.4}},
+                              {"kind": "jastrow1b", "set": 1, "jastrow": {"kind": "gaussian", "alpha": 0.01}}],
+            "potentials": [{"kind": "potentialTwoBody", "sets": [0, 1], "functor": {"kind": "squareWell", "R0": 1.0, "V0": 2.0}},
+                           {"kind": "squareWell2b", "sets": [0, 0], "V0": 1.5, "R0": 0.9},
+                           {"kind": "dipolar2b", "sets": [1, 1], "D": 0.3}],
+            "measurements": [{"kind": "pairCorrelation", "label": "g01", "sets": [0, 1], "bins": 40, "minx": 0, "maxx": 2.5},
+                             {"kind": "pairCorrelation", "label": "g00", "sets": [0, 0], "bins": 30, "minx": 0.1, "maxx": 2.5}]}
+
+
+SPLINE_COEF = [-6.80202700e-05, 3.40101350e-05, -6.80202700e-05, -3.74111485e-04] + [-(0.0101010101 * (i - 1)) ** 2 for i in range(4, 102)]
+
+JASTROWS = {
+    "squareWell": {"kind": "squareWell", "V0": 2.4674011002723395, "R0": 1.0, "Rm": 1.6, "alpha": 0.5, "aInverse": 0.0, "cut_off": 2.5},
+    "hardSphereGauss": {"kind": "hardSphereGauss", "a": 0.05, "Rm": 0.8, "D": 2.0},
+    "poschTeller": {"kind": "poschTeller", "R0": 1.0, "C": 1.0, "alpha": 0.5, "Rm": 1.5, "cut_off": 2.5},
+    "hardSphere": {"kind": "hardSphere", "a": 0.01, "k": 0.6, "cut_off": 2.0},
+    "squareWellBoundState": {"kind": "squareWellBoundState", "V0": 6.0, "R0": 1.0, "Rm": 1.5, "cut_off": 2.5, "aInverse": 0.5, "eb": 0.25, "alpha": 0.7},
+    "bSpline": {"kind": "bSpline", "stepSize": 0.025, "valueRight": -1.0, "derivativeRight": -0.5,
+                "coefficients": [-(0.025 * (i - 1)) ** 2 * 0.16 for i in range(0, 103)]},
+}
+
+
+def structure_factor(N=24, L=4.0):
+    return pbc(N, L, meas=[{"kind": "structureFactor", "label": "sq", "sets": [0, 0], "bins": 16, "maxq": 16 * 2 * np.pi / L,
+                            "lBox": L, "channel": 1},
+                           {"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": 100, "minx": 0, "maxx": L / 2}])
+
+
+def eval_cases():
+    """name -> (cfg, R) for per-configuration parity (1)."""
+    rng = np.random.default_rng(20261017)
+    out = {}
+    for N, L in ((2, 3.0), (3, 3.0), (10, 3.0), (31, 3.2), (32, 3.2), (33, 3.2), (64, 4.0), (65, 4.0), (100, 4.7)):
+        out["pbc_gg_barrier_N%d" % N] = (pbc(N, L), rng.uniform(-L, L, size=(6, 3 * N)))
+    out["pbc_gg_nopot_N40"] = (pbc(40, 3.5, pot=None), rng.uniform(-4, 4, size=(6, 120)))
+    out["pbc_gg_squarewell_N20"] = (pbc(20, 3.0, pot="squareWell"), rng.uniform(-4, 4, size=(6, 60)))
+    out["trap_N10"] = (trap(10), rng.normal(0, 0.7, size=(8, 30)))
+    out["trap_N7"] = (trap(7), rng.normal(0, 0.7, size=(8, 21)))
+    out["mixture"] = (mixture(), rng.uniform(-2.5, 2.5, size=(6, 96)))
+    out["three_body_N16"] = (three_body(16), rng.uniform(-2.5, 2.5, size=(6, 48)))
+    out["three_body_hs_N12"] = (three_body(12, hs=1.6), rng.uniform(-2.5, 2.5, size=(12, 36)))
+    for name, J in JASTROWS.items():
+        N, L = 18, 5.0
+        R = rng.uniform(-2.5, 2.5, size=(6, 3 * N))
+        if name in ("hardSphere",):
+            L = 4.0
+        out["jastrow_" + name] = (pbc(N, L, jastrow=J), R)
+    # lattice configuration: exact minimum-image ties (t/L = +-0.5) in a power-of-two box
+    N, L = 8, 4.0
+    g = np.array([[x, y, z] for x in (0., 2.) for y in (0., 2.) for z in (0., 2.)]).T.reshape(-1)
+    out["lattice_ties_N8"] = (pbc(N, L), np.stack([g, g + 4.0, -g]))
+    return out
+
+
+def dmc_cases():
+    """Small full-DMC runs for statistical parity (2): energies / g(r) within 2 sigma of the reference's CPU run."""
+    t = trap(10, walkers=400)
+    t.update(timeStep=5e-3, stepsPerBlock=200, nBlocks=70, seed=1235, initialConditionGenerator={"lBox": [2.0, 2.0, 2.0]})
+    p = pbc(16, 2.6, walkers=400, meas=[{"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": 26, "minx": 0, "maxx": 1.3}])
+    p.update(timeStep=5e-3, stepsPerBlock=200, nBlocks=70, seed=77)
+    return {"trap_N10": t, "pbc_N16": p}

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz and *.json from the REFERENCE ITSELF (oracle/_ref, built from the
+unmodified /root/reference sources by `make -C oracle ref`).  Run here (the container that has
+/root/reference); the fixtures travel to the GPU box, the reference does not.
+
+    python tests/golden/make_golden.py [--dmc]      (--dmc also re-runs the minutes-long DMC fixtures)
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+from oracle.oracle import REF_BIN, Ref  # noqa: E402
+
+
+def main():
+    ref = Ref()
+    rng = np.random.default_rng(424242)
+    out = {}
+    for name, (cfg, R) in cases.eval_cases().items():
+        r = ref.eval(cfg, R)
+        out[name + "/R"] = R
+        for k, v in r.items():
+            out[name + "/" + k] = v
+    np.savez_compressed(os.path.join(HERE, "eval_cases.npz"), **out)
+
+    pieces = {}
+    # drift-diffusion + Green ratio + histograms on fixed inputs
+    for name in ("pbc_gg_barrier_N33", "mixture", "trap_N10"):
+        cfg, R = cases.eval_cases()[name]
+        e0 = ref.eval(cfg, R)
+        xi = rng.normal(size=R.shape)
+        Rn = ref.drift_diffuse(cfg, cfg["timeStep"], R, e0["grad"], xi)
+        e1 = ref.eval(cfg, Rn)
+        q = ref.green_ratio(cfg, cfg["timeStep"], Rn, e1["grad"], R, e0["grad"])
+        pieces[name + "/xi"] = xi
+        pieces[name + "/Rnew"] = Rn
+        pieces[name + "/q"] = q
+    hist_cases = {"mixture": (cases.mixture(), 2), "three_body_N16": (cases.three_body(16), 1),
+                  "pair_N33": (cases.pbc(33, 3.2, meas=[{"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": 64, "minx": 0, "maxx": 1.6}]), 1)}
+    for name, (cfg, nest) in hist_cases.items():
+        R = rng.uniform(-cfg["lBox"][0] / 2, cfg["lBox"][0] / 2, size=(10, 3 * sum(cfg["N"])))
+        pieces["hist_" + name + "/R"] = R
+        for i in range(nest):
+            bins = cfg["measurements"][i]["bins"]
+            s, w = ref.histogram(cfg, R, i, bins)
+            pieces["hist_%s/sums%d" % (name, i)] = s
+            pieces["hist_%s/weight%d" % (name, i)] = np.asarray([w])
+    # branching with the reference's own RNG (std::ranlux48) and its in-place algorithm
+    for tag, (mean, delta) in {"lower": (40, 10), "upper": (800, 10), "window": (100, 10)}.items():
+        Eo = rng.normal(3.0, 40.0, size=100)
+        En = Eo + rng.normal(0, 5.0, size=100)
+        b = ref.branch(1e-3, mean, delta, 10, En, Eo)
+        pieces["branch_%s/Enew" % tag] = En
+        pieces["branch_%s/Eold" % tag] = Eo
+        pieces["branch_%s/cfg" % tag] = np.asarray([1e-3, mean, delta])
+        for k in ("nDesc", "u", "Eafter"):
+            pieces["branch_%s/%s" % (tag, k)] = b[k]
+        pieces["branch_%s/shifts" % tag] = np.asarray([b["energyShift"], b["energyShiftAfter"]])
+    # planner
+    pops = np.stack([rng.integers(0, 60, size=8) for _ in range(40)])
+    srcs, amts = zip(*[ref.plan(p) for p in pops])
+    pieces["plan/pops"], pieces["plan/sources"], pieces["plan/amounts"] = pops, np.stack(srcs), np.stack(amts)
+    np.savez_compressed(os.path.join(HERE, "pieces.npz"), **pieces)
+
+    if "--dmc" in sys.argv:
+        res = {}
+        for name, cfg in cases.dmc_cases().items():
+            with tempfile.TemporaryDirectory() as tmp:
+                with open(os.path.join(tmp, "input.json"), "w") as f:
+                    json.dump(cfg, f)
+                subprocess.check_call([REF_BIN, "input.json"], cwd=tmp, stdout=subprocess.DEVNULL)
+                e = np.loadtxt(os.path.join(tmp, "energy.dat"), skiprows=1)
+                entry = {"input": cfg, "energy_per_block": e.tolist()}
+                for m in cfg["measurements"]:
+                    blocks = open(os.path.join(tmp, m["label"] + ".dat")).read().strip().split("\n\n")
+                    g = []
+                    for i, b in enumerate(blocks):
+                        rows = [l.split() for l in b.strip().split("\n")]
+                        rows = [r for r in rows if len(r) == 2 and r[0] != "x"]
+                        g.append([float(r[1]) for r in rows])
+                    entry[m["label"] + "_per_block"] = g
+                res[name] = entry
+        with open(os.path.join(HERE, "dmc_reference_runs.json"), "w") as f:
+            json.dump(res, f)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
