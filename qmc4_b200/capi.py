@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqmc4b200.so")
+LIB_PATH = os.environ.get("QMC4_B200_LIB", os.path.join(_HERE, "libqmc4b200.so"))
 
 # qmc_jastrow_kind / qmc_wavefunction_kind / qmc_potential_kind / qmc_estimator_kind
 J_GAUSSIAN, J_GAUSSGAUSS, J_SQUAREWELL, J_HARDSPHEREGAUSS, J_BSPLINE, J_POSCHTELLER, J_HARDSPHERE, J_SQUAREWELL_BOUND = range(1, 9)

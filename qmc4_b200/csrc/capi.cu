@@ -321,6 +321,7 @@ int build_plan(qmc_ctx *c)
         { /* pairCorrelation.cpp:41-59 */
           double nf = std::pow(c->lBox[0], 3) / (dx * 4 * M_PI * P.N[D.setA] * P.N[D.setB]);
           D.norm = (D.setA == D.setB) ? 2 * nf : nf;
+          D.fx_scale = std::ldexp(1.0, 36) * E.maxx * E.maxx;     /* 1/r^2 at r = maxx -> 2^36 */
         }
       else if (E.kind == QMC_EST_TRIMERCORRELATION_UNDIS)
         { /* trimerCorrelation.cpp:128-143 */
@@ -535,7 +536,7 @@ int build_plan(qmc_ctx *c)
   c->cfg.block = 256;
   c->cfg.nwarps_per_group = wpw;
   c->cfg.groups_per_cta = 8 / wpw;
-  c->cfg.smem = group_doubles * 8 * c->cfg.groups_per_cta;
+  c->cfg.smem = group_doubles * 8 * c->cfg.groups_per_cta + (size_t)P.hist_stride * 8;   /* + per-CTA fixed-point histogram */
   if ((int)c->cfg.smem > c->max_smem)
     return fail(c, "configuration needs " + std::to_string(c->cfg.smem) + " B of shared memory per CTA (limit " +
                        std::to_string(c->max_smem) + "): too many particles for this build");
@@ -564,8 +565,10 @@ int ensure_scratch(qmc_ctx *c, size_t bytes, size_t ibytes)
 int grid_for(qmc_ctx *c, int64_t nW)
 {
   // persistent-style grid: a multiple of the SM count (resident CTAs per SM bounded by shared memory)
-  int per_sm = std::max(1, std::min(8, (int)(c->max_smem / std::max<size_t>(c->cfg.smem, 1))));
-  per_sm = std::min(per_sm, 2048 / c->cfg.block);
+  // resident CTAs per SM from the occupancy calculator (registers, shared memory, threads) for the
+  // heavier of the two propagate variants, so that the grid is exactly one resident wave
+  int per_sm = std::min(propagate_occupancy(c->ksel, false, c->cfg.smem), propagate_occupancy(c->ksel, c->has_hist, c->cfg.smem));
+  per_sm = std::max(1, std::min(per_sm, 2048 / c->cfg.block));
   if (const char *e = getenv("QMC4_CTAS_PER_SM"))
     {
       int v = atoi(e);
@@ -1291,6 +1294,7 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "smem_bytes") *value = (double)c->cfg.smem;
   else if (k == "warps_per_walker") *value = c->cfg.nwarps_per_group;
   else if (k == "kernel_variant") *value = c->ksel;
+  else if (k == "ctas_per_sm") *value = propagate_occupancy(c->ksel, c->has_hist, c->cfg.smem);
   else if (k == "launches") *value = (double)c->launches;
   else if (k == "sms") *value = c->sms;
   else if (k == "regs_propagate") *value = propagate_regs(c->ksel, false);

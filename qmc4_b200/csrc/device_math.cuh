@@ -14,15 +14,20 @@ namespace qmc {
 // Minimum image, exactly the reference's  t - std::round(t*Linv)*L  (dmc/geometry.h:50),
 // std::round = half away from zero.  FP64 pipe: 2 (DFMA.RZ + DFMA); FRND.TRUNC runs on the
 // conversion unit and the copysign is one LOP3.
-//   trunc(RZ(t*Linv + copysign(0.5,t)))  ==  round(t*Linv)   [same construction CUDA's round()
-//   uses: DADD.RZ + FRND.TRUNC], with the product folded into the add.  It can differ from the
+//   trunc(RZ(|t|*Linv + 0.5)) == round(|t|*Linv)   [same construction CUDA's round() uses:
+//   DADD.RZ + FRND.TRUNC], with the product folded into the add; round() is odd so the sign of t
+//   is re-applied to the result.  It can differ from the
 //   reference only when fl(t*Linv) is an exact tie but t*Linv is not (or vice versa); for
 //   power-of-two boxes the product is exact and ties (lattice configurations) round identically.
 QMC_DEVICE double min_image(double t, double L, double Linv)
 {
-  double half = __hiloint2double((__double2hiint(t) & 0x80000000) | 0x3fe00000, 0);
-  double n = trunc(__fma_rz(t, Linv, half));
-  return fma(-n, L, t);
+  // work on |t| (free operand modifier on the FP64 pipe) and put the sign back with one LOP3:
+  //   m = trunc(RZ(|t|*Linv + 0.5)) = round-half-away(|t|/L);   d = sign(t) * (|t| - m*L)
+  const double a = fabs(t);
+  const double m = trunc(__fma_rz(a, Linv, 0.5));
+  const double d = fma(-m, L, a);
+  const int hi = __double2hiint(d) ^ (__double2hiint(t) & 0x80000000);
+  return __hiloint2double(hi, __double2loint(d));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -20,6 +20,10 @@
 #include "device_math.cuh"
 #include "jastrows.cuh"
 
+#ifndef QMC_EXP_ESTRIN
+#define QMC_EXP_ESTRIN 0
+#endif
+
 namespace qmc {
 
 struct Group {
@@ -50,9 +54,29 @@ struct EvalResult {
 };
 
 struct HistCtx {
-  double *base;   // this CTA's histogram replica (global memory) or nullptr
-  double w;       // weight of this configuration
+  double *base;        // this CTA's histogram replica (global memory, fp64) or nullptr
+  double w;            // weight of this configuration (a small integer: branching multiplicity or +-1)
+  unsigned *fx;        // this CTA's fixed-point pair histogram in shared memory: lo[stride] then hi[stride], or nullptr
 };
+
+// g(r) accumulation without global atomics on the hot path.  A contribution v = norm/r^2 is
+// quantised to 64-bit fixed point (scale Estimator::fx_scale: a pair at r = maxx maps to 2^36, i.e.
+// 1.5e-11 relative resolution on the smallest contribution) and added to a per-CTA histogram in
+// shared memory with two NATIVE 32-bit shared atomics: the low limb add returns the old value, a
+// wrap of the low limb is forwarded as +1 to the high limb by the thread that caused it, so the
+// final 64-bit total is exact whatever the interleaving (two's complement: negative weights used by
+// the reject/branching corrections cancel the speculative contribution bit for bit).  On B200 a
+// 32-lane RED.F64 to L2 costs ~50 cycles of LSU per warp instruction, the two ATOMS ~10.
+// Contributions >= 2^40 (r < maxx/16) take the exact fp64 global path (rare).
+QMC_DEVICE void hist_add_fixed(unsigned *fx, int stride, int bin, long long x)
+{
+  const unsigned xlo = (unsigned)(unsigned long long)x, xhi = (unsigned)((unsigned long long)x >> 32);
+  const unsigned old = atomicAdd(fx + bin, xlo);
+  const unsigned carry = (old + xlo < old) ? 1u : 0u;
+  if (xhi + carry != 0u) atomicAdd(fx + stride + bin, xhi + carry);
+}
+constexpr double HIST_FX_BYPASS = 1099511627776.0;   // 2^40
+
 
 // ---------------------------------------------------------------------------------------------
 // exp(-alpha*r2) with the scaled-argument constants stored in RadialFn::p[2..14]
@@ -65,41 +89,52 @@ QMC_DEVICE double exp_gg(double r2, const double *p)
   double nd = t - MAGIC;
   double f = fma(nd, -p[3], r2);
   f = fma(nd, -p[4], f);
+#if QMC_EXP_ESTRIN
+  /* Estrin evaluation of 1 + f*(c1 + c2 f + ... + c10 f^9): 13 FP64 ops but only ~6 deep
+     (Horner: 10 ops, 10 deep); c_j = p[4+j] */
+  const double f2 = f * f;
+  const double a0 = fma(p[6], f, p[5]);      /* c1 + c2 f  */
+  const double a1 = fma(p[8], f, p[7]);      /* c3 + c4 f  */
+  const double a2 = fma(p[10], f, p[9]);     /* c5 + c6 f  */
+  const double a3 = fma(p[12], f, p[11]);    /* c7 + c8 f  */
+  const double a4 = fma(p[14], f, p[13]);    /* c9 + c10 f */
+  const double f4 = f2 * f2;
+  const double b0 = fma(a1, f2, a0);
+  const double b1 = fma(a3, f2, a2);
+  const double f8 = f4 * f4;
+  const double c0 = fma(b1, f4, b0);
+  const double rr = fma(a4, f8, c0);
+  double q = fma(rr, f, 1.0);
+#else
   double q = p[14];
 #pragma unroll
   for (int j = 13; j >= 5; --j) q = fma(q, f, p[j]);
   q = fma(q, f, 1.0);
+#endif
+  /* exp(-745) is the smallest double: clamp the exponent instead of flushing (result <= 2^-1000 ~ 1e-301,
+     i.e. zero to every accumulator it can meet); keeps the scaling free of selects */
+  n = max(n, -1000);
   int hi = __double2hiint(q) + (n << 20);
-  double r = __hiloint2double(hi, __double2loint(q));
-  return (n < -1000) ? 0.0 : r;
+  return __hiloint2double(hi, __double2loint(q));
 }
 
-// One fused pair pass: Jastrow JK + pair potential VK (+ g(r) when HIST).
+// One fused pair pass: Jastrow JK + pair potential VK.  (HIST only selects the kernel variant that
+// also runs histogram_pass() on the final configuration; the hot loop is identical.)
 // pair() returns the coefficient g with   grad_row += s*g*d,  grad_col -= s*g*d   (s = grad_scale()).
 template <int JK, int VK, bool HIST> struct PairOp {
   const PairPass &P;
   const double *coef;
-  const Estimator *est;
-  double *hist;
-  double hw;
   double s0 = 0, s1 = 0, vs = 0;
   int cnt = 0;
 
   QMC_DEVICE PairOp(const PairPass &P_, const double *coef_, const Plan &plan, const HistCtx &h) : P(P_), coef(coef_)
   {
-    est = nullptr;
-    hist = nullptr;
-    hw = 0;
-    if (HIST && P.hist >= 0 && h.base)
-      {
-        est = &plan.est[P.hist];
-        hist = h.base + est->offset;
-        hw = h.w * est->norm;
-      }
   }
 
-  QMC_DEVICE double pair(double r2, bool act)
+  // MASKED=false: every lane holds a real pair (full tiles), no select on the hot path
+  template <bool MASKED = true> QMC_DEVICE double pair(double r2, bool act)
   {
+    if (!MASKED) act = true;
     double g = 0;
     const int jk = (JK == J_GENERIC) ? P.J.kind : JK;
     double r = 0;
@@ -107,7 +142,7 @@ template <int JK, int VK, bool HIST> struct PairOp {
     if (JK == J_GAUSSGAUSS)
       { /* u=u0 e, u'/r = -2 u0 a e, lap term = e*(8 a^2 u0 r2 - 12 a u0): sums of e and e*r2 */
         double e = exp_gg(r2, P.J.p);
-        e = act ? e : 0.0;
+        if (MASKED) e = act ? e : 0.0;
         s0 += e;
         s1 = fma(e, r2, s1);
         g = e;
@@ -116,7 +151,6 @@ template <int JK, int VK, bool HIST> struct PairOp {
       { /* u=-a r2, u'/r=-2a, u''=-2a */
         g = act ? 1.0 : 0.0;
         s0 = fma(g, r2, s0);
-        cnt += 0;
       }
     else if (jk != J_NONE)
       {
@@ -140,19 +174,6 @@ template <int JK, int VK, bool HIST> struct PairOp {
         if (!have_r) { r = sqrt(r2); have_r = true; }
         double v = eval_pair_potential(vk, P.v_val, r);
         if (act) vs += v;
-      }
-    if (HIST)
-      {
-        if (hist)
-          { /* pairCorrelation.cpp:24-35 + histogramAccumulator::accumulate (accumulators.h:117) */
-            double y = rsqrt_fast(r2);
-            double rr = r2 * y;
-            if (act && rr < est->maxx)
-              {
-                int b = (int)((rr - est->minx) * est->dxinv);
-                if (b >= 0) atomicAdd(hist + min(b, est->bins - 1), hw * y * y);
-              }
-          }
       }
     return g;
   }
@@ -300,6 +321,174 @@ QMC_DEVICE void pair_tile_rect(Op &op, const Box &box, const double *xa, int nsa
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-stream variants for full 32-wide tiles: the 32 (or 16) rotation steps of a tile are split
+// into NS interleaved streams, each with its own visitor, so one lane works on NS independent
+// pairs at a time (same row particle, columns (l+k+s*STEP) mod 32).  That gives the FP64 pipe NS
+// independent dependency chains per warp (the exp Horner chain is 14 dependent DFMAs) and lets the
+// NS pairs share the loop overhead and the constant loads.
+#ifndef QMC_TILE_STREAMS
+#define QMC_TILE_STREAMS 2
+#endif
+constexpr int TILE_STREAMS = QMC_TILE_STREAMS;
+#ifndef QMC_SHARED_ROWACC
+#define QMC_SHARED_ROWACC 1
+#endif
+
+template <int NS, class Op>
+QMC_DEVICE void pair_tile_rect_ms(Op &op, const Box &box, const double *xa, int nsa, int rbase,
+                                  const double *xb, int nsb, int cbase, int lane, double *acca, double *accb)
+{ /* 32 rows x 32 columns, all lanes active */
+  constexpr int STEPS = 32 / NS;
+  const bool rowok = true;
+  const int p = lane;
+  const double xi = xa[rbase + p], yi = xa[nsa + rbase + p], zi = xa[2 * nsa + rbase + p];
+  double ax[NS], ay[NS], az[NS], vx[NS], vy[NS], vz[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) ax[s] = ay[s] = az[s] = vx[s] = vy[s] = vz[s] = 0.0;
+  const int src = (lane + 1) & 31;
+  const double *xc = xb + cbase, *yc = xb + nsb + cbase, *zc = xb + 2 * nsb + cbase;
+#pragma unroll 1
+  for (int k = 0; k < STEPS; ++k)
+    {
+      if (k > 0)
+        {
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            {
+              vx[s] = shfl_d(vx[s], src);
+              vy[s] = shfl_d(vy[s], src);
+              vz[s] = shfl_d(vz[s], src);
+            }
+        }
+      double dx[NS], dy[NS], dz[NS], r2[NS], g[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        {
+          const int q = (lane + k + s * STEPS) & 31;
+          dx[s] = min_image(xi - xc[q], box.Lx, box.ix);
+          dy[s] = min_image(yi - yc[q], box.Ly, box.iy);
+          dz[s] = min_image(zi - zc[q], box.Lz, box.iz);
+          r2[s] = fma(dz[s], dz[s], fma(dy[s], dy[s], dx[s] * dx[s]));
+        }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) g[s] = op.template pair<false>(r2[s], true);
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        {
+          constexpr int AS = QMC_SHARED_ROWACC ? 0 : 1;   /* one row accumulator for all streams, or one per stream */
+          ax[s * AS] = fma(g[s], dx[s], ax[s * AS]);
+          ay[s * AS] = fma(g[s], dy[s], ay[s * AS]);
+          az[s * AS] = fma(g[s], dz[s], az[s * AS]);
+          vx[s] = fma(-g[s], dx[s], vx[s]);
+          vy[s] = fma(-g[s], dy[s], vy[s]);
+          vz[s] = fma(-g[s], dz[s], vz[s]);
+        }
+    }
+  const double sc = op.grad_scale();
+  if (rowok)
+    {
+      double sx = ax[0], sy = ay[0], sz = az[0];
+#pragma unroll
+      for (int s = 1; s < NS; ++s)
+        {
+          sx += ax[s];
+          sy += ay[s];
+          sz += az[s];
+        }
+      acca[rbase + p] = fma(sc, sx, acca[rbase + p]);
+      acca[nsa + rbase + p] = fma(sc, sy, acca[nsa + rbase + p]);
+      acca[2 * nsa + rbase + p] = fma(sc, sz, acca[2 * nsa + rbase + p]);
+    }
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    { /* after STEPS steps the visitor of stream s belongs to column (lane + STEPS-1 + s*STEPS) */
+      const int q = (lane + STEPS - 1 + s * STEPS) & 31;
+      accb[cbase + q] = fma(sc, vx[s], accb[cbase + q]);
+      accb[nsb + cbase + q] = fma(sc, vy[s], accb[nsb + cbase + q]);
+      accb[2 * nsb + cbase + q] = fma(sc, vz[s], accb[2 * nsb + cbase + q]);
+      __syncwarp();
+    }
+}
+
+template <int NS, class Op>
+QMC_DEVICE void pair_tile_diag_ms(Op &op, const Box &box, const double *xs, int ns, int base, int lane, double *accw)
+{ /* full block of 32: offsets k = 1..16, stream s takes offsets k + s*STEPS, k = 1..STEPS; offset 16 is half-populated */
+  constexpr int STEPS = 16 / NS;
+  const double *xc = xs + base, *yc = xs + ns + base, *zc = xs + 2 * ns + base;
+  const double xi = xc[lane], yi = yc[lane], zi = zc[lane];
+  double ax[NS], ay[NS], az[NS], vx[NS], vy[NS], vz[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) ax[s] = ay[s] = az[s] = vx[s] = vy[s] = vz[s] = 0.0;
+  const int src = (lane + 1) & 31;
+#pragma unroll 1
+  for (int k = 1; k <= STEPS; ++k)
+    {
+      if (k > 1)
+        {
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            {
+              vx[s] = shfl_d(vx[s], src);
+              vy[s] = shfl_d(vy[s], src);
+              vz[s] = shfl_d(vz[s], src);
+            }
+        }
+      double dx[NS], dy[NS], dz[NS], r2[NS], g[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        {
+          const int q = (lane + k + s * STEPS) & 31;
+          dx[s] = min_image(xi - xc[q], box.Lx, box.ix);
+          dy[s] = min_image(yi - yc[q], box.Ly, box.iy);
+          dz[s] = min_image(zi - zc[q], box.Lz, box.iz);
+          r2[s] = fma(dz[s], dz[s], fma(dy[s], dy[s], dx[s] * dx[s]));
+        }
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        {
+          if (s == NS - 1) g[s] = op.template pair<true>(r2[s], !((k == STEPS) && (lane >= 16)));   /* offset 16: half-populated */
+          else g[s] = op.template pair<false>(r2[s], true);
+        }
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        {
+          constexpr int AS = QMC_SHARED_ROWACC ? 0 : 1;   /* one row accumulator for all streams, or one per stream */
+          ax[s * AS] = fma(g[s], dx[s], ax[s * AS]);
+          ay[s * AS] = fma(g[s], dy[s], ay[s * AS]);
+          az[s * AS] = fma(g[s], dz[s], az[s * AS]);
+          vx[s] = fma(-g[s], dx[s], vx[s]);
+          vy[s] = fma(-g[s], dy[s], vy[s]);
+          vz[s] = fma(-g[s], dz[s], vz[s]);
+        }
+    }
+  const double sc = op.grad_scale();
+  {
+    double sx = ax[0], sy = ay[0], sz = az[0];
+#pragma unroll
+    for (int s = 1; s < NS; ++s)
+      {
+        sx += ax[s];
+        sy += ay[s];
+        sz += az[s];
+      }
+    accw[base + lane] = fma(sc, sx, accw[base + lane]);
+    accw[ns + base + lane] = fma(sc, sy, accw[ns + base + lane]);
+    accw[2 * ns + base + lane] = fma(sc, sz, accw[2 * ns + base + lane]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    {
+      const int q = (lane + STEPS + s * STEPS) & 31;
+      accw[base + q] = fma(sc, vx[s], accw[base + q]);
+      accw[ns + base + q] = fma(sc, vy[s], accw[ns + base + q]);
+      accw[2 * ns + base + q] = fma(sc, vz[s], accw[2 * ns + base + q]);
+      __syncwarp();
+    }
+}
+
 // All tiles of one pair pass, distributed round-robin over the warps of the group.
 template <int JK, int VK, bool HIST>
 QMC_DEVICE void run_pair_pass(const Plan &plan, const PairPass &P, const double *coef, const Scratch &S, const Group &G,
@@ -326,12 +515,16 @@ QMC_DEVICE void run_pair_pass(const Plan &plan, const PairPass &P, const double 
               while (b * (b - 1) / 2 > t) --b;
               while ((b + 1) * b / 2 <= t) ++b;
               const int c = t - b * (b - 1) / 2;
-              pair_tile_rect(op, box, xa, nA, b * 32, min(32, nA - b * 32), xa, nA, c * 32, 32, G.lane, acca, acca);
+              const int nrow = min(32, nA - b * 32);
+              if (nrow == 32) pair_tile_rect_ms<TILE_STREAMS>(op, box, xa, nA, b * 32, xa, nA, c * 32, G.lane, acca, acca);
+              else pair_tile_rect(op, box, xa, nA, b * 32, nrow, xa, nA, c * 32, 32, G.lane, acca, acca);
             }
           else
             {
               const int b = t - noff;
-              pair_tile_diag(op, box, xa, nA, b * 32, min(32, nA - b * 32), G.lane, acca);
+              const int nblk = min(32, nA - b * 32);
+              if (nblk == 32) pair_tile_diag_ms<TILE_STREAMS>(op, box, xa, nA, b * 32, G.lane, acca);
+              else pair_tile_diag(op, box, xa, nA, b * 32, nblk, G.lane, acca);
             }
         }
       if (JK == J_GAUSSIAN && G.gtid == 0) lap += -12.0 * P.J.p[0] * (0.5 * (double)nA * (double)(nA - 1));
@@ -342,7 +535,9 @@ QMC_DEVICE void run_pair_pass(const Plan &plan, const PairPass &P, const double 
       for (int t = G.gwarp; t < nba * nbb; t += G.nwarps)
         {
           const int b = t / nbb, c = t - b * nbb;
-          pair_tile_rect(op, box, xa, nA, b * 32, min(32, nA - b * 32), xb, nB, c * 32, min(32, nB - c * 32), G.lane, acca, accb);
+          const int ncol = min(32, nB - c * 32), nrow = min(32, nA - b * 32);
+          if (ncol == 32 && nrow == 32) pair_tile_rect_ms<TILE_STREAMS>(op, box, xa, nA, b * 32, xb, nB, c * 32, G.lane, acca, accb);
+          else pair_tile_rect(op, box, xa, nA, b * 32, nrow, xb, nB, c * 32, ncol, G.lane, acca, accb);
         }
       if (JK == J_GAUSSIAN && G.gtid == 0) lap += -12.0 * P.J.p[0] * ((double)nA * (double)nB);
     }
@@ -525,10 +720,63 @@ QMC_DEVICE EvalResult evaluate_walker(const Plan &plan, const double *coef, cons
   return out;
 }
 
-// Histogram-only pass over the pairs/triplets of the configuration in S.R with weight H.w
-// (corrects the speculative unit-weight accumulation done inside evaluate_walker; see
-// propagate kernel).  Only estimators attached to pair passes / triplet passes are touched.
-QMC_DEVICE void histogram_only(const Plan &plan, const Scratch &S, const Group &G, const HistCtx &H)
+// g(r) pass over the pairs of the FINAL configuration (in S.R) with its branching weight H.w
+// (pairCorrelation::accumulate, pairCorrelation.cpp:17-39, over the post-branching population,
+// dmcDriver.cpp:257-264).  Same tiles as the physics pass but no gradients, so no visitors and no
+// shuffles: lane l holds row particle l and meets column (l+k) mod 32; UNR pairs are in flight per
+// lane.  Bins are filled through hist_add_fixed (shared memory, native 32-bit atomics).
+template <int UNR>
+QMC_DEVICE void hist_tile(const Box &box, const double *xa, int nsa, int rbase, int nr, const double *xb, int nsb, int cbase, int nc,
+                          bool diag, int lane, const Estimator &est, unsigned *fx, double *hist, int stride, int iw, double hw)
+{
+  const bool rowok = lane < nr;
+  const int p = rowok ? lane : 0;
+  const double xi = xa[rbase + p], yi = xa[nsa + rbase + p], zi = xa[2 * nsa + rbase + p];
+  const double *xc = xb + cbase, *yc = xb + nsb + cbase, *zc = xb + 2 * nsb + cbase;
+  const double maxx = est.maxx, minx = est.minx, dxinv = est.dxinv, fxs = est.fx_scale;
+  const int last = est.bins - 1;
+  // diag: offsets 1..nc/2 (cyclic schedule, half-populated last offset when nc is even); else 0..31
+  const int k0 = diag ? 1 : 0, k1 = diag ? (nc >> 1) : 31;
+  for (int kb = k0; kb <= k1; kb += UNR)
+    {
+      double r2[UNR];
+      bool ok[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        {
+          const int k = kb + u;
+          int q = p + k;
+          if (diag) { if (q >= nc) q -= nc; }
+          else q &= 31;
+          ok[u] = rowok && (k <= k1) && (diag ? !((2 * k == nc) && (lane >= (nc >> 1))) : (q < nc));
+          const int qq = ok[u] ? q : 0;
+          const double dx = min_image(xi - xc[qq], box.Lx, box.ix);
+          const double dy = min_image(yi - yc[qq], box.Ly, box.iy);
+          const double dz = min_image(zi - zc[qq], box.Lz, box.iz);
+          r2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
+        }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        {
+          const double y = rsqrt_fast(r2[u]);
+          const double rr = r2[u] * y;
+          const int b = (int)((rr - minx) * dxinv);
+          const double t = y * y * fxs;
+          if (ok[u] && rr < maxx && b >= 0)
+            {
+              if (fx && t < HIST_FX_BYPASS)
+                {
+                  long long x = (long long)t;
+                  if (iw != 1) x *= iw;
+                  hist_add_fixed(fx, stride, min(b, last), x);
+                }
+              else atomicAdd(hist + min(b, last), hw * y * y);
+            }
+        }
+    }
+}
+
+QMC_DEVICE void histogram_pass(const Plan &plan, const Scratch &S, const Group &G, const HistCtx &H)
 {
   const Box box = {plan.L[0], plan.L[1], plan.L[2], plan.Linv[0], plan.Linv[1], plan.Linv[2]};
   for (int t = 0; t < plan.n2b; ++t)
@@ -537,36 +785,62 @@ QMC_DEVICE void histogram_only(const Plan &plan, const Scratch &S, const Group &
       if (P.hist < 0) continue;
       const Estimator &est = plan.est[P.hist];
       double *hist = H.base + est.offset;
+      unsigned *fx = H.fx ? H.fx + est.offset : nullptr;
+      const int iw = (int)H.w;
       const double hw = H.w * est.norm;
       const int nA = plan.N[P.setA], nB = plan.N[P.setB];
       const double *xa = S.R + plan.off[P.setA], *xb = S.R + plan.off[P.setB];
-      const long npairs = (P.setA == P.setB) ? (long)nA * (nA - 1) / 2 : (long)nA * nB;
-      for (long k = G.gtid; k < npairs; k += G.gsize)
+      if (P.setA == P.setB)
         {
-          int a, b;
-          if (P.setA == P.setB)
+          const int nb = (nA + 31) >> 5, noff = nb * (nb - 1) / 2;
+          for (int w = G.gwarp; w < noff + nb; w += G.nwarps)
             {
-              a = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)k)) * 0.5f);
-              while ((long)a * (a - 1) / 2 > k) --a;
-              while ((long)(a + 1) * a / 2 <= k) ++a;
-              b = (int)(k - (long)a * (a - 1) / 2);
+              if (w < noff)
+                {
+                  int b = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)w)) * 0.5f);
+                  while (b * (b - 1) / 2 > w) --b;
+                  while ((b + 1) * b / 2 <= w) ++b;
+                  const int c = w - b * (b - 1) / 2;
+                  hist_tile<4>(box, xa, nA, b * 32, min(32, nA - b * 32), xa, nA, c * 32, 32, false, G.lane, est, fx, hist, plan.hist_stride, iw, hw);
+                }
+              else
+                {
+                  const int b = w - noff, n = min(32, nA - b * 32);
+                  hist_tile<4>(box, xa, nA, b * 32, n, xa, nA, b * 32, n, true, G.lane, est, fx, hist, plan.hist_stride, iw, hw);
+                }
             }
-          else
+        }
+      else
+        {
+          const int nba = (nA + 31) >> 5, nbb = (nB + 31) >> 5;
+          for (int w = G.gwarp; w < nba * nbb; w += G.nwarps)
             {
-              a = (int)(k / nB);
-              b = (int)(k - (long)a * nB);
+              const int b = w / nbb, c = w - b * nbb;
+              hist_tile<4>(box, xa, nA, b * 32, min(32, nA - b * 32), xb, nB, c * 32, min(32, nB - c * 32), false, G.lane, est, fx, hist,
+                           plan.hist_stride, iw, hw);
             }
-          double dx = min_image(xa[a] - xb[b], box.Lx, box.ix);
-          double dy = min_image(xa[nA + a] - xb[nB + b], box.Ly, box.iy);
-          double dz = min_image(xa[2 * nA + a] - xb[2 * nB + b], box.Lz, box.iz);
-          double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-          double y = rsqrt_fast(r2);
-          double rr = r2 * y;
-          if (rr < est.maxx)
-            {
-              int bin = (int)((rr - est.minx) * est.dxinv);
-              if (bin >= 0) atomicAdd(hist + min(bin, est.bins - 1), hw * y * y);
-            }
+        }
+    }
+}
+
+// zero / flush the CTA's fixed-point histogram (all threads of the CTA; callers synchronise)
+QMC_DEVICE void hist_fx_zero(unsigned *fx, int stride)
+{
+  for (int i = threadIdx.x; i < 2 * stride; i += blockDim.x) fx[i] = 0u;
+}
+QMC_DEVICE void hist_fx_flush(const Plan &plan, unsigned *fx, double *replica)
+{
+  const int stride = plan.hist_stride;
+  for (int e = 0; e < plan.nest; ++e)
+    {
+      const Estimator &est = plan.est[e];
+      if (est.fx_scale == 0.0) continue;
+      const double inv = est.norm / est.fx_scale;
+      for (int b = threadIdx.x; b < est.bins; b += blockDim.x)
+        {
+          const unsigned lo = atomicExch(fx + est.offset + b, 0u), hi = atomicExch(fx + stride + est.offset + b, 0u);
+          const long long t = (long long)(((unsigned long long)hi << 32) | (unsigned long long)lo);
+          if (t != 0) atomicAdd(replica + est.offset + b, (double)t * inv);
         }
     }
 }

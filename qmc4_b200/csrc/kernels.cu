@@ -20,6 +20,9 @@ namespace qmc {
 namespace {
 
 constexpr int CTA_THREADS = 256;
+#ifndef QMC_MIN_BLOCKS
+#define QMC_MIN_BLOCKS 2
+#endif
 
 QMC_DEVICE Group make_group(int nwarps_per_group)
 {
@@ -57,7 +60,7 @@ QMC_DEVICE double branch_shift(const DmcParams &dmc, double sumE, double pop)
 
 // ---------------------------------------------------------------------------------------------
 template <int JK, int VK, bool HIST>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, QMC_MIN_BLOCKS)
 eval_kernel(const __grid_constant__ Plan plan, const EvalArgs a, int nwarps_per_group, size_t group_bytes)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -69,13 +72,23 @@ eval_kernel(const __grid_constant__ Plan plan, const EvalArgs a, int nwarps_per_
   HistCtx H;
   H.base = (HIST && a.hist) ? a.hist + (size_t)blockIdx.x * plan.hist_stride : nullptr;
   H.w = 1.0;
+  H.fx = (HIST && a.hist) ? reinterpret_cast<unsigned *>(smem + (size_t)groups * group_bytes) : nullptr;
+  if (HIST && H.fx)
+    {
+      hist_fx_zero(H.fx, plan.hist_stride);
+      __syncthreads();
+    }
   for (long j = (long)blockIdx.x * groups + g; j < a.nW; j += (long)gridDim.x * groups)
     {
       const double *src = a.R + j * dofs;
       for (int k = G.gtid; k < dofs; k += G.gsize) S.R[k] = src[k];
       G.sync();
       EvalResult r = evaluate_walker<JK, VK, HIST>(plan, a.coef, S, G, H);
-      if (HIST && H.base && r.valid) post_estimators(plan, S, G, H);
+      if (HIST && H.base && r.valid)
+        {
+          histogram_pass(plan, S, G, H);
+          post_estimators(plan, S, G, H);
+        }
       double f2 = 0;
       for (int k = G.gtid; k < dofs; k += G.gsize)
         {
@@ -100,11 +113,16 @@ eval_kernel(const __grid_constant__ Plan plan, const EvalArgs a, int nwarps_per_
         }
       G.sync();
     }
+  if (HIST && H.fx)
+    {
+      __syncthreads();
+      hist_fx_flush(plan, H.fx, H.base);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 template <int JK, int VK, bool HIST>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, QMC_MIN_BLOCKS)
 propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams dmc, const StepArgs a,
                  int nwarps_per_group, size_t group_bytes)
 {
@@ -120,7 +138,13 @@ propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
   const unsigned long long step = ctl->step;
   const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
   double *hist_replica = (HIST && a.hist) ? a.hist + (size_t)blockIdx.x * plan.hist_stride : nullptr;
+  unsigned *hist_fx = (HIST && a.hist) ? reinterpret_cast<unsigned *>(smem + (size_t)groups * group_bytes) : nullptr;
   double n_moves = 0, n_acc = 0;
+  if (HIST && hist_fx)
+    {
+      hist_fx_zero(hist_fx, plan.hist_stride);
+      __syncthreads();
+    }
 
   for (int j = blockIdx.x * groups + g; j < nW; j += gridDim.x * groups)
     {
@@ -147,10 +171,11 @@ propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
             }
         }
       G.sync();
-      // ---- evaluate the proposal (speculative unit-weight histogram accumulation on sampling steps)
+      // ---- evaluate the proposal
       HistCtx H;
       H.base = hist_replica;
       H.w = 1.0;
+      H.fx = hist_fx;
       const EvalResult r = evaluate_walker<JK, VK, HIST>(plan, a.coef, S, G, H);
       // ---- log Green ratio and |grad|^2
       double q = 0, f2 = 0;
@@ -235,36 +260,17 @@ propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
         }
       // ---- estimators (sampling steps): the reference accumulates over the POST-branching
       //      population (dmcDriver.cpp:257-264), i.e. the final configuration with weight n.
-      if (HIST && hist_replica)
-        {
+      if (HIST && hist_replica && n > 0)
+        { // S.R must hold the final configuration: the proposal if accepted, the parent otherwise
           G.sync();
-          if (accepted)
+          if (!accepted)
             {
-              if (n != 1)
-                {
-                  HistCtx Hc = {hist_replica, (double)(n - 1)};
-                  histogram_only(plan, S, G, Hc);
-                }
-            }
-          else
-            {
-              HistCtx Hm = {hist_replica, -1.0};
-              histogram_only(plan, S, G, Hm);            // undo the speculative R' contribution
-              G.sync();
               for (int k = G.gtid; k < dofs; k += G.gsize) S.R[k] = Rold[k];
               G.sync();
-              if (n > 0)
-                {
-                  HistCtx Hp = {hist_replica, (double)n};
-                  histogram_only(plan, S, G, Hp);
-                }
             }
-          // estimators that are not fused in the pair pass: S.R holds the final configuration
-          if (n > 0)
-            {
-              HistCtx Hn = {hist_replica, (double)n};
-              post_estimators(plan, S, G, Hn);
-            }
+          HistCtx Hn = {hist_replica, (double)n, hist_fx};
+          histogram_pass(plan, S, G, Hn);
+          post_estimators(plan, S, G, Hn);
         }
       G.sync();
     }
@@ -273,6 +279,11 @@ propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
       double *p = a.partials + ((size_t)blockIdx.x * groups + g) * 2;
       p[0] = n_moves;
       p[1] = n_acc;
+    }
+  if (HIST && hist_fx)
+    {
+      __syncthreads();
+      hist_fx_flush(plan, hist_fx, hist_replica);
     }
 }
 
@@ -297,10 +308,13 @@ scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent
   s_cnt[t] = cnt;
   __syncthreads();
   // total first: the "always keep at least a walker" guard (branching.cpp:29-32) needs it
-  if (t == 0)
-    {
+  if (t < 32)
+    { // warp 0 totals the chunk counts
       int tot = 0;
-      for (int i = 0; i < SCAN_THREADS; ++i) tot += s_cnt[i];
+      for (int i = t; i < SCAN_THREADS; i += 32) tot += s_cnt[i];
+      tot = warp_sum_i(tot);
+      if (t == 0)
+      {
       if (tot == 0 && W > 0)
         {
           a.n_desc[0] = 1;
@@ -308,6 +322,7 @@ scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent
           tot = 1;
         }
       s_total = tot;
+      }
     }
   __syncthreads();
   // exclusive scan of the chunk counts (Hillis-Steele over 1024 entries)
@@ -346,15 +361,32 @@ scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent
       if (t < d) s_e[t] += s_e[t + d];
       __syncthreads();
     }
+  // metropolis counters: per-group partials, fixed-order tree sum
+  __shared__ double s_mv[SCAN_THREADS], s_ac[SCAN_THREADS];
+  {
+    double mv = 0, ac = 0;
+    for (int i = t; i < n_partials; i += SCAN_THREADS)
+      {
+        mv += a.partials[2 * i];
+        ac += a.partials[2 * i + 1];
+      }
+    s_mv[t] = mv;
+    s_ac[t] = ac;
+  }
+  __syncthreads();
+  for (int d = SCAN_THREADS / 2; d >= 1; d >>= 1)
+    {
+      if (t < d)
+        {
+          s_mv[t] += s_mv[t + d];
+          s_ac[t] += s_ac[t + d];
+        }
+      __syncthreads();
+    }
   if (t == 0)
     {
       const int newW = min(s_total, a.cap);
-      double moves = 0, acc = 0;
-      for (int i = 0; i < n_partials; ++i)
-        {
-          moves += a.partials[2 * i];
-          acc += a.partials[2 * i + 1];
-        }
+      const double moves = s_mv[0], acc = s_ac[0];
       ctl->n_prev = W;
       ctl->n_cur = newW;
       if (!init_mode)
@@ -520,6 +552,12 @@ int propagate_regs(int ksel, bool hist)
   if (cudaFuncGetAttributes(&at, prop_ptr(ksel, hist)) != cudaSuccess) return -1;
   return at.numRegs;
 }
+int propagate_occupancy(int ksel, bool hist, size_t smem)
+{
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, prop_ptr(ksel, hist), CTA_THREADS, smem) != cudaSuccess) return 1;
+  return n < 1 ? 1 : n;
+}
 int eval_regs(int ksel, bool hist)
 {
   cudaFuncAttributes at;
@@ -530,7 +568,7 @@ int eval_regs(int ksel, bool hist)
 cudaError_t launch_eval(int ksel, bool hist, const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const EvalArgs &a)
 {
   int nw = cfg.nwarps_per_group;
-  size_t gb = cfg.smem / cfg.groups_per_cta;
+  size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
   void *args[] = {(void *)&plan, (void *)&a, (void *)&nw, (void *)&gb};
   return cudaLaunchKernel(eval_ptr(ksel, hist), dim3(cfg.grid), dim3(cfg.block), args, cfg.smem, st);
 }
@@ -539,7 +577,7 @@ cudaError_t launch_propagate(int ksel, bool hist, const LaunchCfg &cfg, cudaStre
                              const DmcParams &dmc, const StepArgs &a)
 {
   int nw = cfg.nwarps_per_group;
-  size_t gb = cfg.smem / cfg.groups_per_cta;
+  size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
   void *args[] = {(void *)&plan, (void *)&dmc, (void *)&a, (void *)&nw, (void *)&gb};
   return cudaLaunchKernel(prop_ptr(ksel, hist), dim3(cfg.grid), dim3(cfg.block), args, cfg.smem, st);
 }

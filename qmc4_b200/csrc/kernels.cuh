@@ -82,6 +82,7 @@ cudaError_t launch_unpack(cudaStream_t st, const WalkerBuf &buf, int dofs, int f
 cudaError_t configure_kernels(int max_smem_optin);
 int propagate_regs(int ksel, bool hist);
 int eval_regs(int ksel, bool hist);
+int propagate_occupancy(int ksel, bool hist, size_t smem);
 double measure_fp64_peak_tflops(cudaStream_t st, float *ms_out);
 
 } // namespace qmc

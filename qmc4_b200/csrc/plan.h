@@ -65,6 +65,7 @@ struct Estimator {
   double minx, maxx, dxinv;
   double norm;             // pairCorrelation.cpp:41-59 / trimerCorrelation.cpp:128-143 normalisation factor
   double q0, dq;           // structureFactor q-grid (structureFactor.cpp:8-40)
+  double fx_scale;         // pairCorrelation: fixed-point scale of 1/r^2 (2^36 * maxx^2), 0 = fp64 atomics only
 };
 
 struct Plan {
