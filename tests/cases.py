@@ -3,6 +3,8 @@
 Sizes are small enough for the CPU oracle to finish in seconds.  The same dictionaries are fed,
 unchanged, to the reference (oracle/_ref), the C restatement (oracle/qmc_oracle.c) and the CUDA
 product (through the C ABI)."""
+import copy
+
 import numpy as np
 
 GG = {"kind": "gaussiangaussian", "r0": 1.0, "u0": -0.5}
@@ -11,7 +13,7 @@ GG = {"kind": "gaussiangaussian", "r0": 1.0, "u0": -0.5}
 def pbc(N, L, jastrow=GG, pot="potentialBarrier", meas=None, walkers=64, **kw):
     c = {"N": [N], "lBox": [L, L, L], "method": "dmc", "timeStep": 1e-3, "walkers": walkers, "seed": 7,
          "stepsPerBlock": 10, "nBlocks": 1, "correlationSteps": 0,
-         "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": jastrow}],
+         "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": copy.deepcopy(jastrow)}],
          "potentials": [] if pot is None else [{"kind": "potentialTwoBody", "sets": [0, 0], "functor": {"kind": pot, "R0": 1.0, "V0": 2.0}}],
          "measurements": meas or []}
     c.update(kw)
@@ -32,7 +34,7 @@ def three_body(N=16, L=5.0, hs=None, meas=True):
         w3["hardSphereRadius"] = hs
     return {"N": [N], "lBox": [L] * 3, "method": "dmc", "timeStep": 1e-3, "walkers": 32, "seed": 5,
             "stepsPerBlock": 10, "nBlocks": 1, "correlationSteps": 0,
-            "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": GG}, w3],
+            "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": dict(GG)}, w3],
             "potentials": [{"kind": "potentialThreeBodyUnDis", "sets": [0, 0, 0], "functor": {"kind": "squareWell", "R0": 1.5, "V0": 1.0}}],
             "measurements": [{"kind": "trimerCorrelationUnDis", "label": "trimer", "sets": [0], "bins": 50, "minx": 0, "maxx": L / 2}] if meas else []}
 
@@ -40,7 +42,7 @@ def three_body(N=16, L=5.0, hs=None, meas=True):
 def mixture():
     return {"N": [12, 20], "lBox": [5.0, 5.0, 5.0], "method": "dmc", "timeStep": 1e-3, "walkers": 16, "seed": 3,
             "stepsPerBlock": 10, "nBlocks": 1, "correlationSteps": 0,
-            "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": GG},
+            "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": dict(GG)},
                               {"kind": "jastrow2bUnDis", "sets": [1, 1], "jastrow": {"kind": "gaussiangaussian", "r0": 0.8, "u0": -0.3}},
                               {"kind": "jastrow2bDis", "sets": [0, 1], "jastrow": {"kind": "gaussiangaussian", "r0": 1.2, "u0": 0.4}},
                               {"kind": "jastrow1b", "set": 1, "jastrow": {"kind": "gaussian", "alpha": 0.01}}],
