@@ -332,8 +332,13 @@ def main():
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel/config (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[str(args.config)]["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "kernel": "propagate_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "frac": achieved / peak if peak else None, "traffic": traffic,
                 "algorithmic_flop_per_launch": moves_per_launch * flops_per_move, "avg_launch_ms": prop_ms,
                 "peak_source": "FP64 DFMA pipe measured in-process (qmc_get_info fp64_peak_tflops); MEASURED_PEAKS.json carries HBM and bf16 only",
                 "hbm": {"achieved_gbs": moves_per_launch * bytes_per_move / (prop_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
