@@ -583,9 +583,8 @@ int allreduce_sums(qmc_ctx *c)
 {
   if (c->nranks > 1)
     {
+      /* the next propagate kernel derives E_T from gsum itself: one 80-byte collective per step, no extra launch */
       NK(g_nccl.AllReduce(c->ctl->lsum, c->ctl->gsum, 2 + MAX_RANKS, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
-      CK(launch_finalize_shift(c->stream, c->dmc, c->ctl));
-      c->launches += 1;
     }
   return 0;
 }
@@ -1081,7 +1080,13 @@ int qmc_block_results(qmc_ctx *c, qmc_block_result *out)
   out->n_moves = v[2];
   out->n_accepted = v[3];
   out->population = h.n_cur;
-  out->energy_shift = h.eshift;
+  {
+    const DmcParams &D = c->dmc;
+    double e = h.gsum[1] > 0 ? h.gsum[0] / h.gsum[1] : 0.0;
+    if (h.gsum[1] > D.mean_walkers + D.delta_walkers) e += D.log_up;
+    else if (h.gsum[1] < D.mean_walkers - D.delta_walkers) e += D.log_down;
+    out->energy_shift = D.branching_on ? e : 0.0;
+  }
   out->steps_done = h.blk_steps;
   out->overflow = h.overflow;
   out->device_ms = c->device_ms;

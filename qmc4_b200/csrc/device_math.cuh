@@ -30,6 +30,14 @@ QMC_DEVICE double min_image(double t, double L, double Linv)
   return __hiloint2double(hi, __double2loint(d));
 }
 
+// |minimum image| when only r^2 is needed (histogram pass): the sign fix-up is skipped
+QMC_DEVICE double min_image_abs(double t, double L, double Linv)
+{
+  const double a = fabs(t);
+  const double m = trunc(__fma_rz(a, Linv, 0.5));
+  return fma(-m, L, a);
+}
+
 // ---------------------------------------------------------------------------------------------
 // exp(a*g) for a*g <= 0 given the reduced-argument constants of ExpScaled (below).
 // FP64 pipe: 14 (1 DFMA magic, 1 DADD, 2 DFMA Cody-Waite, 10 DFMA Horner); the 2^n scaling is
@@ -127,19 +135,19 @@ QMC_DEVICE double u01_53(uint32_t a, uint32_t b)
 }
 
 // Two N(0,1) deviates from two 32-bit words (Box-Muller).  The transcendental part runs on the
-// FP32/MUFU pipes (logf, sincospif, sqrtf: ~1e-7 relative), the FP64 pipe only sees the two
+// MUFU unit (lg2, sin, cos, sqrt: ~2^-21 absolute error), the FP64 pipe only sees the two
 // conversions: the deviates only seed the proposal R' (dmc/moves/vmcMoves.cpp:31); the Green
-// function ratio is computed from the fp64 positions actually proposed, so detailed balance
-// is not affected by the deviates' precision.
+// function ratio is computed from the fp64 positions actually proposed, so detailed balance does not
+// depend on the deviates' precision.  (x+0.5)*2^-32 in float is exact for small x, so the radial
+// tail reaches sqrt(2*33*ln2) = 6.8 sigma.
 QMC_DEVICE void normal_pair(uint32_t a, uint32_t b, double &z0, double &z1)
 {
-  // (x + 0.5) * 2^-32 in float: exact for small x, so the radial tail reaches sqrt(2*33*ln2) = 6.8 sigma
   float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;
-  float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
+  const float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
   u1 = fminf(u1, 1.0f);
-  float r = sqrtf(-2.0f * logf(u1));
+  const float r = sqrtf(-1.3862943611198906f * __log2f(u1));     /* -2 ln u = -2 ln2 * lg2 u */
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &s, &c);   /* angle in [-pi, pi): best MUFU accuracy */
   z0 = (double)(r * c);
   z1 = (double)(r * s);
 }

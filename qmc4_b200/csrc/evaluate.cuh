@@ -750,9 +750,9 @@ QMC_DEVICE void hist_tile(const Box &box, const double *xa, int nsa, int rbase, 
           else q &= 31;
           ok[u] = rowok && (k <= k1) && (diag ? !((2 * k == nc) && (lane >= (nc >> 1))) : (q < nc));
           const int qq = ok[u] ? q : 0;
-          const double dx = min_image(xi - xc[qq], box.Lx, box.ix);
-          const double dy = min_image(yi - yc[qq], box.Ly, box.iy);
-          const double dz = min_image(zi - zc[qq], box.Lz, box.iz);
+          const double dx = min_image_abs(xi - xc[qq], box.Lx, box.ix);
+          const double dy = min_image_abs(yi - yc[qq], box.Ly, box.iy);
+          const double dz = min_image_abs(zi - zc[qq], box.Lz, box.iz);
           r2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
         }
 #pragma unroll
@@ -772,6 +772,68 @@ QMC_DEVICE void hist_tile(const Box &box, const double *xa, int nsa, int rbase, 
                 }
               else atomicAdd(hist + min(b, last), hw * y * y);
             }
+        }
+    }
+}
+
+// one binned pair (shared by the tile variants below)
+QMC_DEVICE void hist_bin_pair(double r2, bool ok, double maxx, double minx, double dxinv, double fxs, int last, unsigned *fx, double *hist,
+                              int stride, int iw, double hw)
+{
+  const double y = rsqrt_fast(r2);
+  const double rr = r2 * y;
+  const int b = (int)((rr - minx) * dxinv);
+  const double t = y * y * fxs;
+  if (ok && rr < maxx && b >= 0)
+    {
+      if (fx && t < HIST_FX_BYPASS)
+        {
+          long long x = (long long)t;
+          if (iw != 1) x *= iw;
+          hist_add_fixed(fx, stride, min(b, last), x);
+        }
+      else atomicAdd(hist + min(b, last), hw * y * y);
+    }
+}
+
+// Full tiles (32 rows x 32 columns, or a full diagonal block): no predication, incremental column index.
+template <int UNR, bool DIAG>
+QMC_DEVICE void hist_tile_full(const Box &box, const double *xa, int nsa, int rbase, const double *xb, int nsb, int cbase, int lane,
+                               const Estimator &est, unsigned *fx, double *hist, int stride, int iw, double hw)
+{
+  const double xi = xa[rbase + lane], yi = xa[nsa + rbase + lane], zi = xa[2 * nsa + rbase + lane];
+  const double *xc = xb + cbase, *yc = xb + nsb + cbase, *zc = xb + 2 * nsb + cbase;
+  const double maxx = est.maxx, minx = est.minx, dxinv = est.dxinv, fxs = est.fx_scale;
+  const int last = est.bins - 1;
+  // DIAG: offsets 1..15 full + offset 16 half-populated ; else offsets 0..31
+  constexpr int K0 = DIAG ? 1 : 0, NFULL = DIAG ? 15 : 32;
+  static_assert(NFULL % UNR == 0 || DIAG, "unroll must divide 32");
+  int kb = K0;
+  for (; kb + UNR <= K0 + NFULL; kb += UNR)
+    {
+      double r2[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        {
+          const int q = (lane + kb + u) & 31;
+          const double dx = min_image_abs(xi - xc[q], box.Lx, box.ix);
+          const double dy = min_image_abs(yi - yc[q], box.Ly, box.iy);
+          const double dz = min_image_abs(zi - zc[q], box.Lz, box.iz);
+          r2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
+        }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) hist_bin_pair(r2[u], true, maxx, minx, dxinv, fxs, last, fx, hist, stride, iw, hw);
+    }
+  if (DIAG)
+    { /* offsets left over (15 is not a multiple of UNR) and the half-populated offset 16 */
+      for (; kb <= 16; ++kb)
+        {
+          const int q = (lane + kb) & 31;
+          const double dx = min_image_abs(xi - xc[q], box.Lx, box.ix);
+          const double dy = min_image_abs(yi - yc[q], box.Ly, box.iy);
+          const double dz = min_image_abs(zi - zc[q], box.Lz, box.iz);
+          const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+          hist_bin_pair(r2, !(kb == 16 && lane >= 16), maxx, minx, dxinv, fxs, last, fx, hist, stride, iw, hw);
         }
     }
 }
@@ -801,12 +863,14 @@ QMC_DEVICE void histogram_pass(const Plan &plan, const Scratch &S, const Group &
                   while (b * (b - 1) / 2 > w) --b;
                   while ((b + 1) * b / 2 <= w) ++b;
                   const int c = w - b * (b - 1) / 2;
-                  hist_tile<4>(box, xa, nA, b * 32, min(32, nA - b * 32), xa, nA, c * 32, 32, false, G.lane, est, fx, hist, plan.hist_stride, iw, hw);
+                  if (nA - b * 32 >= 32) hist_tile_full<4, false>(box, xa, nA, b * 32, xa, nA, c * 32, G.lane, est, fx, hist, plan.hist_stride, iw, hw);
+                  else hist_tile<4>(box, xa, nA, b * 32, nA - b * 32, xa, nA, c * 32, 32, false, G.lane, est, fx, hist, plan.hist_stride, iw, hw);
                 }
               else
                 {
                   const int b = w - noff, n = min(32, nA - b * 32);
-                  hist_tile<4>(box, xa, nA, b * 32, n, xa, nA, b * 32, n, true, G.lane, est, fx, hist, plan.hist_stride, iw, hw);
+                  if (n == 32) hist_tile_full<5, true>(box, xa, nA, b * 32, xa, nA, b * 32, G.lane, est, fx, hist, plan.hist_stride, iw, hw);
+                  else hist_tile<4>(box, xa, nA, b * 32, n, xa, nA, b * 32, n, true, G.lane, est, fx, hist, plan.hist_stride, iw, hw);
                 }
             }
         }

@@ -134,7 +134,8 @@ propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
   const int dofs = plan.dofs;
   const Ctl *ctl = a.ctl;
   const int nW = ctl->n_cur;
-  const double eT = ctl->eshift;
+  /* E_T from the (all-reduced) sums of the population this step starts from (branching.cpp:65-97) */
+  const double eT = dmc.branching_on ? branch_shift(dmc, ctl->gsum[0], ctl->gsum[1]) : 0.0;
   const unsigned long long step = ctl->step;
   const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
   double *hist_replica = (HIST && a.hist) ? a.hist + (size_t)blockIdx.x * plan.hist_stride : nullptr;
@@ -288,81 +289,92 @@ propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
 }
 
 // ---------------------------------------------------------------------------------------------
-// Branching bookkeeping, single CTA.  Thread t owns the contiguous chunk [t*C,(t+1)*C) of the
-// walkers just propagated; sums are combined in a fixed order (deterministic).
+// Branching bookkeeping, single CTA of 1024 threads.  Walkers are consumed in tiles of 4096 with
+// coalesced 16-byte loads (4 consecutive walkers per thread), an in-register prefix over the 4, a
+// shuffle scan inside each warp and a 32-entry scan of the warp totals; a running carry links the
+// tiles.  All floating-point sums are combined in a fixed order (deterministic).
 constexpr int SCAN_THREADS = 1024;
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent_next, int n_partials, int multi_rank, int init_mode)
 {
-  __shared__ int s_cnt[SCAN_THREADS];
-  __shared__ double s_e[SCAN_THREADS];
-  __shared__ int s_total;
+  __shared__ int s_warp[32];
+  __shared__ double s_e[SCAN_THREADS], s_mv[SCAN_THREADS], s_ac[SCAN_THREADS];
+  __shared__ int s_carry, s_tile;
   Ctl *ctl = a.ctl;
   const int W = ctl->n_cur;
-  const int t = threadIdx.x;
-  const int C = (W + SCAN_THREADS - 1) / SCAN_THREADS;
-  const int lo = min(W, t * C), hi = min(W, lo + C);
-  int cnt = 0;
-  for (int j = lo; j < hi; ++j) cnt += a.n_desc[j];
-  s_cnt[t] = cnt;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_carry = 0;
   __syncthreads();
-  // total first: the "always keep at least a walker" guard (branching.cpp:29-32) needs it
-  if (t < 32)
-    { // warp 0 totals the chunk counts
-      int tot = 0;
-      for (int i = t; i < SCAN_THREADS; i += 32) tot += s_cnt[i];
-      tot = warp_sum_i(tot);
-      if (t == 0)
-      {
-      if (tot == 0 && W > 0)
-        {
-          a.n_desc[0] = 1;
-          s_cnt[0] = 1;
-          tot = 1;
-        }
-      s_total = tot;
-      }
-    }
-  __syncthreads();
-  // exclusive scan of the chunk counts (Hillis-Steele over 1024 entries)
-  int v = s_cnt[t];
-  __syncthreads();
-  for (int d = 1; d < SCAN_THREADS; d <<= 1)
-    {
-      int add = (t >= d) ? s_cnt[t - d] : 0;
-      __syncthreads();
-      s_cnt[t] += add;
-      __syncthreads();
-    }
-  int off = s_cnt[t] - v;
   double esum = 0;
   int dropped = 0;
-  for (int j = lo; j < hi; ++j)
+  for (int base = 0; base < W; base += 4 * SCAN_THREADS)
     {
-      const int n = a.n_desc[j];
-      const double e = a.out.E[j];
-      for (int c = 0; c < n; ++c)
+      const int j0 = base + 4 * t;
+      int n[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) n[u] = (j0 + u < W) ? a.n_desc[j0 + u] : 0;
+      const int mine = n[0] + n[1] + n[2] + n[3];
+      int inc = mine;                                   /* inclusive scan inside the warp */
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
         {
-          if (off < a.cap)
-            {
-              parent_next[off] = j;
-              esum += e;
-            }
-          else dropped = 1;
-          ++off;
+          const int v = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += v;
         }
-    }
-  s_e[t] = esum;
-  if (dropped) ctl->overflow = 1;
-  __syncthreads();
-  for (int d = SCAN_THREADS / 2; d >= 1; d >>= 1)
-    {
-      if (t < d) s_e[t] += s_e[t + d];
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      if (warp == 0)
+        {
+          int w = s_warp[lane], wi = w;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1)
+            {
+              const int v = __shfl_up_sync(0xffffffffu, wi, d);
+              if (lane >= d) wi += v;
+            }
+          s_warp[lane] = wi - w;                        /* exclusive offsets of the warps */
+          if (lane == 31) s_tile = wi;                  /* tile total */
+        }
+      __syncthreads();
+      int off = s_carry + s_warp[warp] + (inc - mine);
+      const int tile_total = s_tile;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        {
+          const int j = j0 + u;
+          if (n[u] > 0)
+            {
+              const double e = a.out.E[j];
+              for (int c = 0; c < n[u]; ++c)
+                {
+                  if (off < a.cap)
+                    {
+                      parent_next[off] = j;
+                      esum += e;
+                    }
+                  else dropped = 1;
+                  ++off;
+                }
+            }
+        }
+      __syncthreads();
+      if (t == 0) s_carry += tile_total;
       __syncthreads();
     }
-  // metropolis counters: per-group partials, fixed-order tree sum
-  __shared__ double s_mv[SCAN_THREADS], s_ac[SCAN_THREADS];
+  int total = s_carry;
+  if (total == 0 && W > 0)
+    { /* always keep at least a walker (branching.cpp:29-32) */
+      if (t == 0)
+        {
+          a.n_desc[0] = 1;
+          parent_next[0] = 0;
+          esum = a.out.E[0];
+        }
+      total = 1;
+    }
+  if (dropped) ctl->overflow = 1;
+  // fixed-order tree sums: energies, metropolis counters (per-group partials)
   {
     double mv = 0, ac = 0;
     for (int i = t; i < n_partials; i += SCAN_THREADS)
@@ -370,6 +382,7 @@ scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent
         mv += a.partials[2 * i];
         ac += a.partials[2 * i + 1];
       }
+    s_e[t] = esum;
     s_mv[t] = mv;
     s_ac[t] = ac;
   }
@@ -378,6 +391,7 @@ scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent
     {
       if (t < d)
         {
+          s_e[t] += s_e[t + d];
           s_mv[t] += s_mv[t + d];
           s_ac[t] += s_ac[t + d];
         }
@@ -385,7 +399,7 @@ scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent
     }
   if (t == 0)
     {
-      const int newW = min(s_total, a.cap);
+      const int newW = min(total, a.cap);
       const double moves = s_mv[0], acc = s_ac[0];
       ctl->n_prev = W;
       ctl->n_cur = newW;

@@ -7,8 +7,9 @@ __global__ void __launch_bounds__(256) k(double *ghist, int iters, int active_la
 {
   __shared__ unsigned long long sh64[1024];
   __shared__ unsigned sh32[1024];
+  __shared__ unsigned sh32b[1024];
   __shared__ double shd[4][1024];
-  for (int i = threadIdx.x; i < 1024; i += 256) { sh64[i] = 0; sh32[i] = 0; for (int w = 0; w < 4; ++w) shd[w][i] = 0; }
+  for (int i = threadIdx.x; i < 1024; i += 256) { sh64[i] = 0; sh32[i] = 0; sh32b[i] = 0; for (int w = 0; w < 4; ++w) shd[w][i] = 0; }
   __syncthreads();
   unsigned s = threadIdx.x * 7919u + blockIdx.x * 104729u + 1;
   double *rep = ghist + (size_t)blockIdx.x * 1024;
@@ -35,10 +36,30 @@ __global__ void __launch_bounds__(256) k(double *ghist, int iters, int active_la
             }
         }
       if (MODE == 5) { acc += v; }   // baseline loop cost
+      if (MODE == 6)
+        { // two-limb fixed point with carry (the scheme of evaluate.cuh)
+          if (act)
+            {
+              const long long x = (long long)(v * 68719476736.0);
+              const unsigned xlo = (unsigned)(unsigned long long)x, xhi = (unsigned)((unsigned long long)x >> 32);
+              const unsigned old = atomicAdd(&sh32[b], xlo);
+              const unsigned carry = (old + xlo < old) ? 1u : 0u;
+              atomicAdd(&sh32b[b], xhi + carry);
+            }
+        }
+      if (MODE == 7)
+        { // two independent limbs, no return value
+          if (act)
+            {
+              const long long x = (long long)(v * 68719476736.0);
+              atomicAdd(&sh32[b], (unsigned)(x & 0xfffff));
+              atomicAdd(&sh32b[b], (unsigned)(x >> 20));
+            }
+        }
     }
   __syncthreads();
   if (MODE != 0)
-    for (int i = threadIdx.x; i < 1000; i += 256) rep[i] += (double)sh64[i] + sh32[i] + shd[0][i] + shd[warp & 3][i] + acc;
+    for (int i = threadIdx.x; i < 1000; i += 256) rep[i] += (double)sh64[i] + sh32[i] + sh32b[i] + shd[0][i] + shd[warp & 3][i] + acc;
 }
 template <int MODE> void run(double *g, const char *name, int active)
 {
@@ -69,7 +90,8 @@ int main()
       run<1>(g, "ATOMS u64 shared", a);
       run<2>(g, "ATOMS u32 shared", a);
       run<3>(g, "atomicAdd double shared (CAS)", a);
-      run<4>(g, "match.any + private smem RMW", a);
+      run<6>(g, "2-limb fixed point with carry", a);
+      run<7>(g, "2 independent limbs no return", a);
     }
   return 0;
 }

@@ -101,7 +101,7 @@ def eval_cases():
 def dmc_cases():
     """Small full-DMC runs for statistical parity (2): energies / g(r) within 2 sigma of the reference's CPU run."""
     t = trap(10, walkers=400)
-    t.update(timeStep=5e-3, stepsPerBlock=200, nBlocks=70, seed=1235, initialConditionGenerator={"lBox": [2.0, 2.0, 2.0]})
+    t.update(timeStep=5e-3, stepsPerBlock=200, nBlocks=160, seed=1235, initialConditionGenerator={"lBox": [2.0, 2.0, 2.0]})
     p = pbc(16, 2.6, walkers=400, meas=[{"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": 26, "minx": 0, "maxx": 1.3}])
-    p.update(timeStep=5e-3, stepsPerBlock=200, nBlocks=70, seed=77)
+    p.update(timeStep=5e-3, stepsPerBlock=200, nBlocks=160, seed=77)
     return {"trap_N10": t, "pbc_N16": p}
