@@ -10,7 +10,6 @@ import pytest
 
 import cases
 
-pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "qmc4_b200", "host", "dmc_b200")
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -32,6 +31,7 @@ def _blocked_error(x):
     return max(errs)
 
 
+@pytest.mark.gpu
 def test_unchanged_input_json_runs_and_matches_reference_statistics(tmp_path):
     fx = json.load(open(os.path.join(GOLD, "dmc_reference_runs.json")))["pbc_N16"]
     cfg = fx["input"]
@@ -73,6 +73,9 @@ def test_unchanged_input_json_runs_and_matches_reference_statistics(tmp_path):
 
 
 def test_errors_follow_the_reference(tmp_path):
+    """factory and input errors are raised before any device work: checked on CPU"""
+    if not os.path.exists(BIN):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "qmc4_b200", "host")])
     cfg = cases.pbc(8, 4.0, walkers=8)
     cfg["wavefunctions"][0]["jastrow"]["kind"] = "nonexistent"
     p = run(cfg, str(tmp_path))
@@ -81,8 +84,27 @@ def test_errors_follow_the_reference(tmp_path):
     del cfg["correlationSteps"]
     p = run(cfg, str(tmp_path))
     assert p.returncode != 0 and "correlationSteps" in p.stderr                  # required key (main.cpp:287)
+    cfg = cases.pbc(8, 4.0, walkers=8, method="vmc")
+    p = run(cfg, str(tmp_path))
+    assert p.returncode != 0 and "vmc" in p.stderr                               # single-walker VMC stays on the CPU code
+    cfg = cases.pbc(8, 4.0, walkers=8)
+    cfg["lBox"] = [4.0, 4.0]
+    p = run(cfg, str(tmp_path))
+    assert p.returncode != 0 and "dimensionality" in p.stderr                    # main.cpp:173-177
+    cfg = cases.pbc(8, 4.0, walkers=8)
+    cfg["wavefunctions"][0]["sets"] = [0, 1]
+    cfg["N"] = [4, 4]
+    p = run(cfg, str(tmp_path))
+    assert p.returncode != 0 and "setA != setB" in p.stderr                      # jastrowWavefunctionTwoBody.h:100
+    json.dump({"kind": "gaussiangaussian", "r0": 1.0, "u0": -0.5}, open(tmp_path / "jastrow.json", "w"))
+    cfg = cases.pbc(8, 4.0, walkers=8)
+    cfg["wavefunctions"][0]["jastrow"] = "@jastrow.json"                          # "@file" links (input.cpp:7-34)
+    cfg["potentials"][0]["functor"]["kind"] = "nonexistent"
+    p = run(cfg, str(tmp_path))
+    assert p.returncode != 0 and "potentialTwoBody/nonexistent" in p.stderr      # link resolved, ids built in key order
 
 
+@pytest.mark.gpu
 def test_multi_gpu_threads(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
