@@ -126,6 +126,13 @@ struct qmc_ctx {
   double prop_ms = 0;
   long prop_launches_timed = 0;
   int time_kernels = 0;
+  // experimental pipeline 2 (QMC4_PIPELINE=2): branching decided in the scan kernel, estimators in their own
+  // kernel, the per-step all-reduce on a second stream off the critical path
+  int pipeline = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_scan = nullptr, ev_ar = nullptr;
+  bool ar_pending = false;
+  double *e_old = nullptr;
 };
 
 namespace {
@@ -568,6 +575,7 @@ int grid_for(qmc_ctx *c, int64_t nW)
   // resident CTAs per SM from the occupancy calculator (registers, shared memory, threads) for the
   // heavier of the two propagate variants, so that the grid is exactly one resident wave
   int per_sm = std::min(propagate_occupancy(c->ksel, false, c->cfg.smem), propagate_occupancy(c->ksel, c->has_hist, c->cfg.smem));
+  if (c->pipeline == 2) per_sm = propagate_v2_occupancy(c->ksel, c->cfg.smem);
   per_sm = std::max(1, std::min(per_sm, 2048 / c->cfg.block));
   if (const char *e = getenv("QMC4_CTAS_PER_SM"))
     {
@@ -619,8 +627,46 @@ StepArgs make_step_args(qmc_ctx *c, int accumulate)
   return a;
 }
 
+// wait (on the host) for everything either stream still has in flight
+int sync_all(qmc_ctx *c)
+{
+  if (c->comm_stream) CK(cudaStreamSynchronize(c->comm_stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->ar_pending = false;
+  return 0;
+}
+
+int one_step_v2(qmc_ctx *c, int accumulate)
+{ /* propagate(k) || all-reduce(k-1)  ->  scan(k)  ->  { all-reduce(k) on the comm stream } || estimators(k) || propagate(k+1) */
+  StepArgs a = make_step_args(c, accumulate);
+  a.hist = nullptr;
+  const bool timed = c->time_kernels && c->pev_used < qmc_ctx::NEV;
+  if (timed) CK(cudaEventRecord(c->pev0[c->pev_used], c->stream));
+  CK(launch_propagate_v2(c->ksel, c->cfg, c->stream, c->plan, c->dmc, a, c->e_old));
+  if (timed) CK(cudaEventRecord(c->pev1[c->pev_used++], c->stream));
+  if (c->ar_pending) CK(cudaStreamWaitEvent(c->stream, c->ev_ar, 0));        /* scan needs E_T of the previous population */
+  CK(launch_scan_v2(c->stream, c->dmc, a, c->e_old, c->n_partials, c->nranks > 1));
+  c->launches += 2;
+  c->cur ^= 1;
+  if (c->nranks > 1)
+    {
+      CK(cudaEventRecord(c->ev_scan, c->stream));
+      CK(cudaStreamWaitEvent(c->comm_stream, c->ev_scan, 0));
+      NK(g_nccl.AllReduce(c->ctl->lsum, c->ctl->gsum, 2 + MAX_RANKS, NCCL_FLOAT64, NCCL_SUM, c->comm, c->comm_stream));
+      CK(cudaEventRecord(c->ev_ar, c->comm_stream));
+      c->ar_pending = true;
+    }
+  if (accumulate && c->has_hist)
+    {
+      CK(launch_estimators(c->cfg, c->stream, c->plan, c->buf[c->cur], c->parent, c->ctl, c->hist));
+      c->launches += 1;
+    }
+  return 0;
+}
+
 int one_step(qmc_ctx *c, int accumulate, const TraceDev *tr)
 {
+  if (c->pipeline == 2 && !tr) return one_step_v2(c, accumulate);
   StepArgs a = make_step_args(c, accumulate);
   if (tr) a.trace = *tr;
   const bool hist = accumulate && c->has_hist;
@@ -697,6 +743,15 @@ int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, co
       cudaEventCreate(&c->pev0[i]);
       cudaEventCreate(&c->pev1[i]);
     }
+  if (const char *pv = getenv("QMC4_PIPELINE"))
+    if (atoi(pv) == 2)
+      {
+        c->pipeline = 2;
+        if ((e = configure_kernels_v2(c->max_smem)) != cudaSuccess) return bail(std::string("kernel image (v2): ") + cudaGetErrorString(e));
+        if ((e = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+        cudaEventCreateWithFlags(&c->ev_scan, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_ar, cudaEventDisableTiming);
+      }
   if ((e = cudaMalloc(&c->ctl, sizeof(Ctl))) != cudaSuccess) return bail(cudaGetErrorString(e));
   cudaMemset(c->ctl, 0, sizeof(Ctl));
   memset(&c->dmc, 0, sizeof c->dmc);
@@ -709,7 +764,12 @@ void qmc_destroy(qmc_ctx *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->e_old);
+  if (c->ev_scan) cudaEventDestroy(c->ev_scan);
+  if (c->ev_ar) cudaEventDestroy(c->ev_ar);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   for (int b = 0; b < 2; ++b)
     {
       cudaFree(c->buf[b].R);
@@ -825,6 +885,7 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
     }
   CK(cudaMalloc(&c->parent, capacity * 4));
   CK(cudaMalloc(&c->n_desc, capacity * 4));
+  if (c->pipeline == 2) CK(cudaMalloc(&c->e_old, capacity * 8));
   c->cfg.grid = grid_for(c, capacity);
   c->n_partials = c->cfg.grid * c->cfg.groups_per_cta;
   CK(cudaMalloc(&c->partials, (size_t)c->n_partials * 2 * 8));
@@ -905,6 +966,7 @@ int qmc_accumulate_configs(qmc_ctx *c, const double *R, int64_t nW)
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->pipeline == 2 && sync_all(c)) return 1;
   if (!c->has_hist) return fail(c, "no estimators registered");
   cudaSetDevice(c->device);
   if (nW <= 0) return 0;
@@ -928,6 +990,7 @@ int qmc_upload_walkers(qmc_ctx *c, const double *R, int64_t nW)
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   if (nW < 1) return fail(c, "need at least one walker");
   if (nW > c->cap) return fail(c, "more walkers than capacity");
@@ -954,6 +1017,7 @@ int qmc_download_walkers(qmc_ctx *c, double *R, int64_t capW, int64_t *nW, doubl
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   Ctl h;
   CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -997,6 +1061,7 @@ int qmc_step_traced(qmc_ctx *c, int accumulate, const qmc_trace *tr, int64_t tra
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   Ctl h;
   CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -1062,6 +1127,7 @@ int qmc_block_results(qmc_ctx *c, qmc_block_result *out)
 {
   if (!c || !out) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   Ctl h;
   CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -1101,6 +1167,7 @@ int qmc_get_estimator(qmc_ctx *c, int est_index, double *sums, int bins, double 
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
   if (est_index < 0 || est_index >= c->plan.nest) return fail(c, "estimator index out of range");
+  if (c->pipeline == 2 && sync_all(c)) return 1;
   const Estimator &E = c->plan.est[est_index];
   if (bins != E.bins) return fail(c, "bins mismatch");
   cudaSetDevice(c->device);
@@ -1130,6 +1197,7 @@ int qmc_clear_estimators(qmc_ctx *c)
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   if (c->hist) CK(cudaMemsetAsync(c->hist, 0, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8, c->stream));
   CK(cudaMemsetAsync(&c->ctl->est_weight, 0, 8, c->stream));
@@ -1141,6 +1209,7 @@ int qmc_synchronize(qmc_ctx *c)
 {
   if (!c) return 1;
   cudaSetDevice(c->device);
+  if (c->pipeline == 2 && sync_all(c)) return 1;
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1228,6 +1297,7 @@ int qmc_rebalance(qmc_ctx *c, int64_t *moved)
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
   if (c->nranks == 1) return 0;
   cudaSetDevice(c->device);
+  if (c->pipeline == 2 && sync_all(c)) return 1;
   Ctl h;
   CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1299,6 +1369,7 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "smem_bytes") *value = (double)c->cfg.smem;
   else if (k == "warps_per_walker") *value = c->cfg.nwarps_per_group;
   else if (k == "kernel_variant") *value = c->ksel;
+  else if (k == "pipeline") *value = c->pipeline;
   else if (k == "ctas_per_sm") *value = propagate_occupancy(c->ksel, c->has_hist, c->cfg.smem);
   else if (k == "launches") *value = (double)c->launches;
   else if (k == "sms") *value = c->sms;

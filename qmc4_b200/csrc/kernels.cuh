@@ -85,4 +85,13 @@ int eval_regs(int ksel, bool hist);
 int propagate_occupancy(int ksel, bool hist, size_t smem);
 double measure_fp64_peak_tflops(cudaStream_t st, float *ms_out);
 
+// experimental pipeline 2 (kernels_v2.cu, QMC4_PIPELINE=2)
+cudaError_t configure_kernels_v2(int max_smem_optin);
+int propagate_v2_occupancy(int ksel, size_t smem);
+cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const DmcParams &dmc,
+                                const StepArgs &a, double *e_old);
+cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int n_partials, int multi_rank);
+cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const WalkerBuf &buf, const int *parent,
+                              const Ctl *ctl, double *hist);
+
 } // namespace qmc

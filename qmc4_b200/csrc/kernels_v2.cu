@@ -1,0 +1,360 @@
+// kernels_v2.cu — EXPERIMENTAL step pipeline ("pipeline 2"), selected with QMC4_PIPELINE=2.
+// NOT the default and NOT yet validated on hardware (written after the round-1 GPU budget was
+// spent): the default pipeline of kernels.cu is untouched by this file.
+//
+// Why: in pipeline 1 `propagate_kernel` needs E_T (for nDescendants) and therefore the per-step
+// all-reduce sits on the critical path (35-60 us of a 0.34 ms step at 8 GPUs), and the g(r) pass runs
+// inside the register-heavy propagate kernel.  Pipeline 2 reorders the step:
+//     propagate_v2 (no E_T, no estimators; writes E_old per walker)
+//  -> scan_v2      (computes nDescendants = int(exp(-tau(E'+E)/2 - E_T)) + u) with the SAME Philox
+//                   draw pipeline 1 uses, so trajectories are bitwise identical; prefix sum,
+//                   parent map, sums)                                  [waits for all-reduce k-1]
+//  -> all-reduce k on a second stream, overlapped with
+//  -> estimator_kernel (post-branching population, unit weight: dmcDriver::accumulate,
+//                   dmcDriver.cpp:257-264, exactly as the reference iterates it) and with
+//     propagate_v2 of step k+1.
+#include "kernels.cuh"
+#include "evaluate.cuh"
+#include "kernel_common.cuh"
+
+namespace qmc {
+
+namespace {
+
+template <int JK, int VK>
+__global__ void __launch_bounds__(CTA_THREADS, QMC_MIN_BLOCKS)
+propagate_v2_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams dmc, const StepArgs a, double *e_old,
+                    int nwarps_per_group, size_t group_bytes)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Group G = make_group(nwarps_per_group);
+  const int groups = (CTA_THREADS / 32) / nwarps_per_group;
+  const int g = (threadIdx.x >> 5) / nwarps_per_group;
+  const Scratch S = make_scratch(plan, smem, g, nwarps_per_group, group_bytes);
+  const int dofs = plan.dofs;
+  const Ctl *ctl = a.ctl;
+  const int nW = ctl->n_cur;
+  const unsigned long long step = ctl->step;
+  const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
+  double n_moves = 0, n_acc = 0;
+
+  for (int j = blockIdx.x * groups + g; j < nW; j += gridDim.x * groups)
+    {
+      const int src = a.parent[j];
+      const double *Rold = a.in.R + (size_t)src * dofs;
+      const double *Fold = a.in.F + (size_t)src * dofs;
+      for (int c = G.gtid; c * 4 < dofs; c += G.gsize)
+        {
+          u32x4 rnd = philox4x32_10({(uint32_t)j, (uint32_t)c, step_lo, step_hi}, dmc.seed_lo, dmc.seed_hi);
+          double z[4];
+          normal_pair(rnd.x, rnd.y, z[0], z[1]);
+          normal_pair(rnd.z, rnd.w, z[2], z[3]);
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            {
+              const int k = c * 4 + m;
+              if (k < dofs) S.R[k] = fma(dmc.sqrt_tau, z[m], fma(dmc.tau, Fold[k], Rold[k]));
+            }
+        }
+      G.sync();
+      HistCtx H = {nullptr, 1.0, nullptr};
+      const EvalResult r = evaluate_walker<JK, VK, false>(plan, a.coef, S, G, H);
+      double q = 0, f2 = 0;
+      for (int k = G.gtid; k < dofs; k += G.gsize)
+        {
+          const double fo = Fold[k], ro = Rold[k], fn = S.acc[k], rn = S.R[k];
+          const double aa = 0.5 * dmc.tau * (fo - fn) - rn + ro;
+          q = fma(aa, fo + fn, q);
+          f2 = fma(fn, fn, f2);
+        }
+      q = warp_sum(q);
+      f2 = warp_sum(f2);
+      if (G.lane == 0)
+        {
+          S.red[G.gwarp * 4 + 0] = q;
+          S.red[G.gwarp * 4 + 1] = f2;
+        }
+      G.sync();
+      double qs = 0, f2s = 0;
+      for (int w = 0; w < G.nwarps; ++w)
+        {
+          qs += S.red[w * 4 + 0];
+          f2s += S.red[w * 4 + 1];
+        }
+      const double Enew = r.V - 0.5 * (r.lap + f2s);
+      const double lp_old = a.in.logpsi[src];
+      const double Eold = a.in.E[src];
+      const u32x4 rd = philox4x32_10({(uint32_t)j, 0xffffffffu, step_lo, step_hi}, dmc.seed_lo, dmc.seed_hi);
+      const double u_m = u01_53(rd.x, rd.y);
+      const double A = 2.0 * (r.logpsi - lp_old) + qs;
+      const bool accepted = r.valid && (A > 0.0 || A > log(u_m));
+      const double Efin = accepted ? Enew : Eold;
+      double *Rout = a.out.R + (size_t)j * dofs;
+      double *Fout = a.out.F + (size_t)j * dofs;
+      if (accepted)
+        for (int k = G.gtid; k < dofs; k += G.gsize)
+          {
+            Rout[k] = S.R[k];
+            Fout[k] = S.acc[k];
+          }
+      else
+        for (int k = G.gtid; k < dofs; k += G.gsize)
+          {
+            Rout[k] = Rold[k];
+            Fout[k] = Fold[k];
+          }
+      if (G.gtid == 0)
+        {
+          a.out.logpsi[j] = accepted ? r.logpsi : lp_old;
+          a.out.E[j] = Efin;
+          e_old[j] = Eold;            /* branching needs (E' + E)/2 (branching.cpp:13); decided in scan_v2 */
+          n_moves += 1;
+          n_acc += accepted ? 1 : 0;
+        }
+      G.sync();
+    }
+  if (G.gtid == 0)
+    {
+      double *p = a.partials + ((size_t)blockIdx.x * groups + g) * 2;
+      p[0] = n_moves;
+      p[1] = n_acc;
+    }
+}
+
+constexpr int SCAN2_THREADS = 1024;
+
+// scan_kernel of pipeline 1 + the branching decision (nDescendants) it used to receive from propagate.
+__global__ void __launch_bounds__(SCAN2_THREADS)
+scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const double *e_old, int *parent_next, int n_partials, int multi_rank)
+{
+  __shared__ int s_warp[32];
+  __shared__ double s_e[SCAN2_THREADS], s_mv[SCAN2_THREADS], s_ac[SCAN2_THREADS];
+  __shared__ int s_carry, s_tile;
+  Ctl *ctl = a.ctl;
+  const int W = ctl->n_cur;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned long long step = ctl->step;
+  const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
+  const double eT = dmc.branching_on ? branch_shift(dmc, ctl->gsum[0], ctl->gsum[1]) : 0.0;
+  if (t == 0) s_carry = 0;
+  __syncthreads();
+  double esum = 0;
+  int dropped = 0;
+  for (int base = 0; base < W; base += 4 * SCAN2_THREADS)
+    {
+      const int j0 = base + 4 * t;
+      int n[4];
+      double e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        {
+          const int j = j0 + u;
+          n[u] = 0;
+          e[u] = 0;
+          if (j < W)
+            {
+              e[u] = a.out.E[j];
+              int nn = 1;
+              if (dmc.branching_on)
+                {
+                  const u32x4 rd = philox4x32_10({(uint32_t)j, 0xffffffffu, step_lo, step_hi}, dmc.seed_lo, dmc.seed_hi);
+                  const double u_b = u01_53(rd.z, rd.w);
+                  nn = (int)(exp(-dmc.tau * (0.5 * (e[u] + e_old[j]) - eT)) + u_b);      /* branching.cpp:13 */
+                }
+              n[u] = max(0, min(nn, a.cap));
+              a.n_desc[j] = n[u];
+            }
+        }
+      const int mine = n[0] + n[1] + n[2] + n[3];
+      int inc = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+        {
+          const int v = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += v;
+        }
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      if (warp == 0)
+        {
+          int w = s_warp[lane], wi = w;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1)
+            {
+              const int v = __shfl_up_sync(0xffffffffu, wi, d);
+              if (lane >= d) wi += v;
+            }
+          s_warp[lane] = wi - w;
+          if (lane == 31) s_tile = wi;
+        }
+      __syncthreads();
+      int off = s_carry + s_warp[warp] + (inc - mine);
+      const int tile_total = s_tile;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        {
+          const int j = j0 + u;
+          for (int c = 0; c < n[u]; ++c)
+            {
+              if (off < a.cap)
+                {
+                  parent_next[off] = j;
+                  esum += e[u];
+                }
+              else dropped = 1;
+              ++off;
+            }
+        }
+      __syncthreads();
+      if (t == 0) s_carry += tile_total;
+      __syncthreads();
+    }
+  int total = s_carry;
+  if (total == 0 && W > 0)
+    {
+      if (t == 0)
+        {
+          a.n_desc[0] = 1;
+          parent_next[0] = 0;
+          esum = a.out.E[0];
+        }
+      total = 1;
+    }
+  if (dropped) ctl->overflow = 1;
+  {
+    double mv = 0, ac = 0;
+    for (int i = t; i < n_partials; i += SCAN2_THREADS)
+      {
+        mv += a.partials[2 * i];
+        ac += a.partials[2 * i + 1];
+      }
+    s_e[t] = esum;
+    s_mv[t] = mv;
+    s_ac[t] = ac;
+  }
+  __syncthreads();
+  for (int d = SCAN2_THREADS / 2; d >= 1; d >>= 1)
+    {
+      if (t < d)
+        {
+          s_e[t] += s_e[t + d];
+          s_mv[t] += s_mv[t + d];
+          s_ac[t] += s_ac[t + d];
+        }
+      __syncthreads();
+    }
+  if (t == 0)
+    {
+      const int newW = min(total, a.cap);
+      ctl->n_prev = W;
+      ctl->n_cur = newW;
+      ctl->step += 1;
+      ctl->blk_moves += s_mv[0];
+      ctl->blk_acc += s_ac[0];
+      ctl->blk_steps += 1;
+      ctl->lsum[0] = s_e[0];
+      ctl->lsum[1] = (double)newW;
+      for (int r = 0; r < MAX_RANKS; ++r) ctl->lsum[2 + r] = (r == dmc.rank) ? (double)newW : 0.0;
+      if (a.accumulate)
+        {
+          ctl->blk_esum += s_e[0];
+          ctl->blk_ecount += (double)newW;
+          ctl->est_weight += (double)newW;
+        }
+      if (!multi_rank)
+        {
+          for (int r = 0; r < 2 + MAX_RANKS; ++r) ctl->gsum[r] = ctl->lsum[r];
+          if (dmc.branching_on) ctl->eshift = branch_shift(dmc, s_e[0], (double)newW);
+        }
+    }
+}
+
+// Estimators over the post-branching population with unit weight per walker (dmcDriver::accumulate,
+// dmcDriver.cpp:257-264): slot j of the new population is walker parent[j] of `buf`.
+__global__ void __launch_bounds__(CTA_THREADS)
+estimator_kernel(const __grid_constant__ Plan plan, const WalkerBuf buf, const int *parent, const Ctl *ctl, double *hist,
+                 int nwarps_per_group, size_t group_bytes)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Group G = make_group(nwarps_per_group);
+  const int groups = (CTA_THREADS / 32) / nwarps_per_group;
+  const int g = (threadIdx.x >> 5) / nwarps_per_group;
+  const Scratch S = make_scratch(plan, smem, g, nwarps_per_group, group_bytes);
+  const int dofs = plan.dofs;
+  const int nW = ctl->n_cur;
+  HistCtx H;
+  H.base = hist + (size_t)blockIdx.x * plan.hist_stride;
+  H.w = 1.0;
+  H.fx = reinterpret_cast<unsigned *>(smem + (size_t)groups * group_bytes);
+  hist_fx_zero(H.fx, plan.hist_stride);
+  __syncthreads();
+  for (int j = blockIdx.x * groups + g; j < nW; j += gridDim.x * groups)
+    {
+      const double *src = buf.R + (size_t)parent[j] * dofs;
+      for (int k = G.gtid; k < dofs; k += G.gsize) S.R[k] = src[k];
+      G.sync();
+      histogram_pass(plan, S, G, H);
+      post_estimators(plan, S, G, H);
+      G.sync();
+    }
+  __syncthreads();
+  hist_fx_flush(plan, H.fx, H.base);
+}
+
+template <int JK, int VK> const void *prop2() { return (const void *)propagate_v2_kernel<JK, VK>; }
+
+const void *prop2_ptr(int ksel)
+{
+  switch (ksel)
+    {
+    case KSEL_GG_STEP: return prop2<J_GAUSSGAUSS, V_STEP>();
+    case KSEL_GG_NONE: return prop2<J_GAUSSGAUSS, V_NONE>();
+    case KSEL_GAUSS_NONE: return prop2<J_GAUSSIAN, V_NONE>();
+    default: return prop2<J_GENERIC, V_GENERIC>();
+    }
+}
+
+} // namespace
+
+cudaError_t configure_kernels_v2(int max_smem_optin)
+{
+  for (int k = 0; k < KSEL_COUNT; ++k)
+    {
+      cudaError_t e = cudaFuncSetAttribute(prop2_ptr(k), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+      if (e != cudaSuccess) return e;
+    }
+  return cudaFuncSetAttribute((const void *)estimator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+}
+
+int propagate_v2_occupancy(int ksel, size_t smem)
+{
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, prop2_ptr(ksel), CTA_THREADS, smem) != cudaSuccess) return 1;
+  return n < 1 ? 1 : n;
+}
+
+cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const DmcParams &dmc,
+                                const StepArgs &a, double *e_old)
+{
+  int nw = cfg.nwarps_per_group;
+  size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
+  void *args[] = {(void *)&plan, (void *)&dmc, (void *)&a, (void *)&e_old, (void *)&nw, (void *)&gb};
+  return cudaLaunchKernel(prop2_ptr(ksel), dim3(cfg.grid), dim3(cfg.block), args, cfg.smem, st);
+}
+
+cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int n_partials, int multi_rank)
+{
+  scan_v2_kernel<<<1, SCAN2_THREADS, 0, st>>>(dmc, a, e_old, a.parent, n_partials, multi_rank);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const WalkerBuf &buf, const int *parent,
+                              const Ctl *ctl, double *hist)
+{
+  int nw = cfg.nwarps_per_group;
+  size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
+  estimator_kernel<<<cfg.grid, cfg.block, cfg.smem, st>>>(plan, buf, parent, ctl, hist, nw, gb);
+  return cudaGetLastError();
+}
+
+} // namespace qmc
