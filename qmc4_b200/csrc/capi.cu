@@ -81,6 +81,7 @@ struct EstTerm { int kind; std::vector<int> sets; int bins; double minx, maxx; s
 
 struct qmc_ctx {
   int device = 0;
+  bool planning_only = false;      // device -1: term-list compiler only (host logic tests); every compute entry point refuses
   int sms = 0, max_smem = 0;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -707,6 +708,20 @@ int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, co
       g_create_error = "nSpecies must be in 1.." + std::to_string(MAX_SPECIES);
       return 1;
     }
+  if (device == -1)
+    { /* planning-only context: builds and exposes the kernel plan without touching CUDA (B200 limits assumed) */
+      qmc_ctx *p = new qmc_ctx;
+      p->device = -1;
+      p->planning_only = true;
+      p->sms = 148;
+      p->max_smem = 232448;
+      for (int d = 0; d < 3; ++d) p->lBox[d] = lBox[d];
+      p->N.assign(N, N + nSpecies);
+      memset(&p->dmc, 0, sizeof p->dmc);
+      p->dmc.nranks = 1;
+      *out = p;
+      return 0;
+    }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -763,6 +778,11 @@ int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, co
 void qmc_destroy(qmc_ctx *c)
 {
   if (!c) return;
+  if (c->planning_only)
+    {
+      delete c;
+      return;
+    }
   cudaSetDevice(c->device);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
@@ -858,7 +878,7 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
 {
   if (!c) return 1;
   if (c->planned) return fail(c, "qmc_set_dmc called twice");
-  cudaSetDevice(c->device);
+  if (!c->planning_only) cudaSetDevice(c->device);
   if (build_plan(c)) return 1;
   DmcParams &D = c->dmc;
   D.tau = timeStep;
@@ -875,6 +895,12 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
   D.nranks = c->nranks;
   if (capacity <= 0) capacity = 2 * (targetWalkers + deltaWalkers) / std::max(1, c->nranks) + 64;
   c->cap = capacity;
+  if (c->planning_only)
+    {
+      c->cfg.grid = c->sms * 2;
+      c->planned = true;
+      return 0;
+    }
   const size_t dofs = c->plan.dofs;
   for (int b = 0; b < 2; ++b)
     {
@@ -935,6 +961,7 @@ int qmc_eval_device(qmc_ctx *c, const double *dR, int64_t nW, double *dlogpsi, d
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   cudaSetDevice(c->device);
   if (nW <= 0) return 0;
   return eval_common(c, dR, nW, dlogpsi, dgrad, dlap, dV, dE, dvalid, false, 0);
@@ -944,6 +971,7 @@ int qmc_eval(qmc_ctx *c, const double *R, int64_t nW, double *logpsi, double *gr
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   cudaSetDevice(c->device);
   if (nW <= 0) return 0;
   const size_t dofs = c->plan.dofs;
@@ -966,6 +994,7 @@ int qmc_accumulate_configs(qmc_ctx *c, const double *R, int64_t nW)
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   if (c->pipeline == 2 && sync_all(c)) return 1;
   if (!c->has_hist) return fail(c, "no estimators registered");
   cudaSetDevice(c->device);
@@ -990,6 +1019,7 @@ int qmc_upload_walkers(qmc_ctx *c, const double *R, int64_t nW)
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   if (nW < 1) return fail(c, "need at least one walker");
@@ -1017,6 +1047,7 @@ int qmc_download_walkers(qmc_ctx *c, double *R, int64_t capW, int64_t *nW, doubl
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   Ctl h;
@@ -1040,6 +1071,7 @@ int qmc_step(qmc_ctx *c, int nSteps, int sampleEvery)
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   cudaSetDevice(c->device);
   if (sampleEvery < 1) sampleEvery = 1;
   CK(cudaEventRecord(c->ev0, c->stream));
@@ -1061,6 +1093,7 @@ int qmc_step_traced(qmc_ctx *c, int accumulate, const qmc_trace *tr, int64_t tra
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   Ctl h;
@@ -1127,6 +1160,7 @@ int qmc_block_results(qmc_ctx *c, qmc_block_result *out)
 {
   if (!c || !out) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   Ctl h;
@@ -1166,6 +1200,7 @@ int qmc_get_estimator(qmc_ctx *c, int est_index, double *sums, int bins, double 
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   if (est_index < 0 || est_index >= c->plan.nest) return fail(c, "estimator index out of range");
   if (c->pipeline == 2 && sync_all(c)) return 1;
   const Estimator &E = c->plan.est[est_index];
@@ -1197,6 +1232,7 @@ int qmc_clear_estimators(qmc_ctx *c)
 {
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   if (c->pipeline == 2 && sync_all(c)) return 1;
   cudaSetDevice(c->device);
   if (c->hist) CK(cudaMemsetAsync(c->hist, 0, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8, c->stream));
@@ -1208,6 +1244,7 @@ int qmc_clear_estimators(qmc_ctx *c)
 int qmc_synchronize(qmc_ctx *c)
 {
   if (!c) return 1;
+  if (c->planning_only) return 0;
   cudaSetDevice(c->device);
   if (c->pipeline == 2 && sync_all(c)) return 1;
   CK(cudaStreamSynchronize(c->stream));
@@ -1237,6 +1274,7 @@ int qmc_comm_unique_id(void *uniqueId128)
 int qmc_comm_init(qmc_ctx *c, const void *uniqueId128, int rank, int nranks)
 {
   if (!c) return 1;
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no communicator");
   if (c->planned) return fail(c, "qmc_comm_init must precede qmc_set_dmc");
   if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return fail(c, "invalid rank/nranks (max 8 ranks)");
   cudaSetDevice(c->device);
@@ -1295,6 +1333,7 @@ int qmc_rebalance(qmc_ctx *c, int64_t *moved)
   if (!c) return 1;
   if (moved) *moved = 0;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   if (c->nranks == 1) return 0;
   cudaSetDevice(c->device);
   if (c->pipeline == 2 && sync_all(c)) return 1;
@@ -1362,7 +1401,79 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
 {
   if (!c || !key || !value) return 1;
   const std::string k = key;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  {
+    /* plan introspection (host logic tests): "pass<i>.<field>", "onebody<i>.<field>", "triplet<i>.<field>", "est<i>.<field>" */
+    int idx = -1;
+    char fld[32] = {0};
+    const Plan &P = c->plan;
+    if (sscanf(key, "pass%d.%31s", &idx, fld) == 2 && idx >= 0 && idx < P.n2b)
+      {
+        const PairPass &T = P.p2[idx];
+        const std::string f = fld;
+        int pi = -1;
+        if (f == "setA") *value = T.setA;
+        else if (f == "setB") *value = T.setB;
+        else if (f == "jkind") *value = T.J.kind;
+        else if (f == "vkind") *value = T.vkind;
+        else if (f == "hist") *value = T.hist;
+        else if (f == "v_val") *value = T.v_val;
+        else if (f == "v_thr2") *value = T.v_thr2;
+        else if (sscanf(fld, "p%d", &pi) == 1 && pi >= 0 && pi < NJP) *value = T.J.p[pi];
+        else return fail(c, "unknown info key " + k);
+        return 0;
+      }
+    if (sscanf(key, "onebody%d.%31s", &idx, fld) == 2 && idx >= 0 && idx < P.n1b)
+      {
+        const OneBodyTerm &T = P.t1[idx];
+        const std::string f = fld;
+        if (f == "set") *value = T.set;
+        else if (f == "jkind") *value = T.J.kind;
+        else if (f == "has_pot") *value = T.has_pot;
+        else if (f == "half_omega2") *value = T.half_omega2;
+        else return fail(c, "unknown info key " + k);
+        return 0;
+      }
+    if (sscanf(key, "triplet%d.%31s", &idx, fld) == 2 && idx >= 0 && idx < P.n3b)
+      {
+        const TripletPass &T = P.p3[idx];
+        const std::string f = fld;
+        if (f == "set") *value = T.set;
+        else if (f == "jkind") *value = T.J.kind;
+        else if (f == "has_pot") *value = T.has_pot;
+        else if (f == "hist") *value = T.hist;
+        else if (f == "has_constraint") *value = T.has_constraint;
+        else if (f == "v_val") *value = T.v_val;
+        else return fail(c, "unknown info key " + k);
+        return 0;
+      }
+    if (sscanf(key, "est%d.%31s", &idx, fld) == 2 && idx >= 0 && idx < P.nest)
+      {
+        const Estimator &T = P.est[idx];
+        const std::string f = fld;
+        if (f == "kind") *value = T.kind;
+        else if (f == "bins") *value = T.bins;
+        else if (f == "offset") *value = T.offset;
+        else if (f == "norm") *value = T.norm;
+        else if (f == "dxinv") *value = T.dxinv;
+        else if (f == "q0") *value = T.q0;
+        else if (f == "dq") *value = T.dq;
+        else if (f == "fx_scale") *value = T.fx_scale;
+        else return fail(c, "unknown info key " + k);
+        return 0;
+      }
+  }
+  if (c->planning_only && (k == "regs_propagate" || k == "regs_eval" || k == "fp64_peak_tflops" || k == "ctas_per_sm" || k.rfind("time_kernels", 0) == 0 ||
+                           k.rfind("propagate_", 0) == 0))
+    return fail(c, "planning-only context (device -1): " + k + " needs a device");
   if (k == "dofs") *value = c->plan.dofs;
+  else if (k == "n_one_body") *value = c->plan.n1b;
+  else if (k == "n_triplet_passes") *value = c->plan.n3b;
+  else if (k == "n_estimators") *value = c->plan.nest;
+  else if (k == "hist_stride") *value = c->plan.hist_stride;
+  else if (k == "groups_per_cta") *value = c->cfg.groups_per_cta;
+  else if (k == "log_up") *value = c->dmc.log_up;
+  else if (k == "log_down") *value = c->dmc.log_down;
   else if (k == "capacity") *value = (double)c->cap;
   else if (k == "grid") *value = c->cfg.grid;
   else if (k == "block") *value = c->cfg.block;
