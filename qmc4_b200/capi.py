@@ -48,6 +48,11 @@ def load():
             "qmc4_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback)" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
+    if hasattr(lib, "qmc_emulated") and os.environ.get("QMC4_B200_ALLOW_EMULATION") != "tests-only":
+        # tests/emu builds the CUDA sources for a CPU thread emulator to test kernel logic without a
+        # GPU; it is test infrastructure and must never be picked up as the product library
+        raise ImportError("qmc4_b200: %s is the tests/emu emulation build, not the CUDA library "
+                          "(there is no CPU fallback)" % LIB_PATH)
     vp = C.c_void_p
     lib.qmc_last_error.restype = C.c_char_p
     lib.qmc_last_error.argtypes = [vp]

@@ -1059,7 +1059,7 @@ int qmc_download_walkers(qmc_ctx *c, double *R, int64_t capW, int64_t *nW, doubl
   if (n > capW) return fail(c, "download buffer too small");
   const size_t dofs = c->plan.dofs;
   if (ensure_scratch(c, (size_t)n * (dofs + 1) * 8, 0)) return 1;
-  gather_kernel<<<(int)n, 128, 0, c->stream>>>(c->buf[c->cur], c->parent, (int)dofs, (int)n, c->scr, c->scr + n * dofs);
+  QMC_LAUNCH(gather_kernel, (int)n, 128, 0, c->stream, c->buf[c->cur], c->parent, (int)dofs, (int)n, c->scr, c->scr + n * dofs);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(R, c->scr, n * dofs * 8, cudaMemcpyDeviceToHost, c->stream));
   if (E) CK(cudaMemcpyAsync(E, c->scr + n * dofs, n * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -9,6 +9,11 @@
 namespace qmc {
 
 #define QMC_DEVICE __device__ __forceinline__
+#ifdef QMC_EMULATE   /* tests/emu host build: libstdc++ uses the token __noinline__ itself */
+#define QMC_NOINLINE __attribute__((noinline))
+#else
+#define QMC_NOINLINE __noinline__
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Minimum image, exactly the reference's  t - std::round(t*Linv)*L  (dmc/geometry.h:50),
@@ -93,7 +98,11 @@ QMC_DEVICE double exp_neg(double x)
 QMC_DEVICE double rsqrt_fast(double x)
 {
   double y = __hiloint2double(0, 0);
+#ifdef QMC_EMULATE   /* tests/emu: host build of the kernels, test infrastructure only */
+  y = (double)(1.0f / sqrtf((float)x));
+#else
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#endif
   double y2 = y * y;
   double e = fma(-x, y2, 1.0);                 // 1 - x*y^2
   double h = fma(e, 0.375, 0.5);               // 1/2 + 3/8 e
@@ -181,7 +190,11 @@ QMC_DEVICE int warp_sum_i(int v)
 // barrier over one walker group (a set of whole warps inside the CTA); id 1..15
 QMC_DEVICE void group_sync(int bar_id, int nthreads)
 {
+#ifdef QMC_EMULATE
+  emu::barrier(bar_id, nthreads);
+#else
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+#endif
 }
 
 } // namespace qmc

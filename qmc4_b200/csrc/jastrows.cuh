@@ -21,7 +21,7 @@
 namespace qmc {
 
 // u, u', u'' at distance r.  `coef` = spline coefficient pool (global memory, read-only).
-static __device__ __noinline__ void eval_radial(const RadialFn &J, const double *__restrict__ coef, double r,
+static __device__ QMC_NOINLINE void eval_radial(const RadialFn &J, const double *__restrict__ coef, double r,
                                          double &d0, double &d1, double &d2)
 {
   const double *p = J.p;
@@ -206,7 +206,7 @@ static __device__ __noinline__ void eval_radial(const RadialFn &J, const double 
 }
 
 // pair potential at distance r for the kinds that need r itself (generic path)
-static __device__ __noinline__ double eval_pair_potential(int vkind, double v_val, double r)
+static __device__ QMC_NOINLINE double eval_pair_potential(int vkind, double v_val, double r)
 {
   switch (vkind)
     {

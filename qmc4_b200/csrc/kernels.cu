@@ -25,7 +25,7 @@ template <int JK, int VK, bool HIST>
 __global__ void __launch_bounds__(CTA_THREADS, QMC_MIN_BLOCKS)
 eval_kernel(const __grid_constant__ Plan plan, const EvalArgs a, int nwarps_per_group, size_t group_bytes)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
+  QMC_DYNAMIC_SMEM(smem);
   const Group G = make_group(nwarps_per_group);
   const int groups = (CTA_THREADS / 32) / nwarps_per_group;
   const int g = (threadIdx.x >> 5) / nwarps_per_group;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(CTA_THREADS, QMC_MIN_BLOCKS)
 propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams dmc, const StepArgs a,
                  int nwarps_per_group, size_t group_bytes)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
+  QMC_DYNAMIC_SMEM(smem);
   const Group G = make_group(nwarps_per_group);
   const int groups = (CTA_THREADS / 32) / nwarps_per_group;
   const int g = (threadIdx.x >> 5) / nwarps_per_group;
@@ -473,10 +473,25 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+#ifdef QMC_EMULATE   /* tests/emu: cudaLaunchKernel gets a trampoline that unpacks the argument array */
+template <int JK, int VK, bool HIST> struct KernelPtrs {
+  static void eval_tramp(void **p)
+  {
+    eval_kernel<JK, VK, HIST>(*(Plan *)p[0], *(EvalArgs *)p[1], *(int *)p[2], *(size_t *)p[3]);
+  }
+  static void prop_tramp(void **p)
+  {
+    propagate_kernel<JK, VK, HIST>(*(Plan *)p[0], *(DmcParams *)p[1], *(StepArgs *)p[2], *(int *)p[3], *(size_t *)p[4]);
+  }
+  static const void *eval() { return (const void *)&eval_tramp; }
+  static const void *prop() { return (const void *)&prop_tramp; }
+};
+#else
 template <int JK, int VK, bool HIST> struct KernelPtrs {
   static const void *eval() { return (const void *)eval_kernel<JK, VK, HIST>; }
   static const void *prop() { return (const void *)propagate_kernel<JK, VK, HIST>; }
 };
+#endif
 
 const void *eval_ptr(int ksel, bool hist)
 {
@@ -562,38 +577,38 @@ cudaError_t launch_scan(cudaStream_t st, const DmcParams &dmc, const StepArgs &a
 {
   // the parent map written here is consumed by the NEXT propagate; it lives behind a.parent's twin
   int *parent_next = a.parent;
-  scan_kernel<<<1, SCAN_THREADS, 0, st>>>(dmc, a, parent_next, n_partials, multi_rank, init_mode);
+  QMC_LAUNCH(scan_kernel, 1, SCAN_THREADS, 0, st, dmc, a, parent_next, n_partials, multi_rank, init_mode);
   return cudaGetLastError();
 }
 
 cudaError_t launch_finalize_shift(cudaStream_t st, const DmcParams &dmc, Ctl *ctl)
 {
-  finalize_shift_kernel<<<1, 32, 0, st>>>(dmc, ctl);
+  QMC_LAUNCH(finalize_shift_kernel, 1, 32, 0, st, dmc, ctl);
   return cudaGetLastError();
 }
 
 cudaError_t launch_init_identity(cudaStream_t st, int *parent, int *n_desc, int n, Ctl *ctl)
 {
-  init_identity_kernel<<<(n + 255) / 256 + 1, 256, 0, st>>>(parent, n_desc, n, ctl);
+  QMC_LAUNCH(init_identity_kernel, (n + 255) / 256 + 1, 256, 0, st, parent, n_desc, n, ctl);
   return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_hist(cudaStream_t st, const double *hist, int replicas, int stride, double *out)
 {
-  reduce_hist_kernel<<<(stride + 127) / 128, 128, 0, st>>>(hist, replicas, stride, out);
+  QMC_LAUNCH(reduce_hist_kernel, (stride + 127) / 128, 128, 0, st, hist, replicas, stride, out);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pack(cudaStream_t st, const WalkerBuf &buf, const int *parent, int dofs, int first, int count, double *slab)
 {
   if (count <= 0) return cudaSuccess;
-  pack_kernel<<<count, 128, 0, st>>>(buf, parent, dofs, first, count, slab);
+  QMC_LAUNCH(pack_kernel, count, 128, 0, st, buf, parent, dofs, first, count, slab);
   return cudaGetLastError();
 }
 cudaError_t launch_unpack(cudaStream_t st, const WalkerBuf &buf, int dofs, int first, int count, const double *slab)
 {
   if (count <= 0) return cudaSuccess;
-  unpack_kernel<<<count, 128, 0, st>>>(buf, dofs, first, count, slab);
+  QMC_LAUNCH(unpack_kernel, count, 128, 0, st, buf, dofs, first, count, slab);
   return cudaGetLastError();
 }
 
@@ -612,7 +627,7 @@ double measure_fp64_peak_tflops(cudaStream_t st, float *ms_out)
   for (int rep = 0; rep < 5; ++rep)
     {
       cudaEventRecord(e0, st);
-      fp64_peak_kernel<<<grid, 256, 0, st>>>(out, iters, 0.999999, 1e-9);
+      QMC_LAUNCH(fp64_peak_kernel, grid, 256, 0, st, out, iters, 0.999999, 1e-9);
       cudaEventRecord(e1, st);
       cudaEventSynchronize(e1);
       float ms = 0;

@@ -3,6 +3,17 @@
 #include "plan.h"
 #include <cuda_runtime.h>
 
+// Dynamic shared memory of a kernel / a <<<>>> launch.  The QMC_EMULATE branches exist only for the
+// CPU thread emulation of tests/emu (test infrastructure; never compiled into libqmc4b200.so).
+#ifdef QMC_EMULATE
+#define QMC_DYNAMIC_SMEM(name) unsigned char *name = emu::tls.dyn_smem
+#define QMC_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  emu::launch_lambda(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#define QMC_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define QMC_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 namespace qmc {
 
 // One walker buffer (HBM, SoA over walkers; each walker's dofs doubles are contiguous in the

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(CTA_THREADS, QMC_MIN_BLOCKS)
 propagate_v2_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams dmc, const StepArgs a, double *e_old,
                     int nwarps_per_group, size_t group_bytes)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
+  QMC_DYNAMIC_SMEM(smem);
   const Group G = make_group(nwarps_per_group);
   const int groups = (CTA_THREADS / 32) / nwarps_per_group;
   const int g = (threadIdx.x >> 5) / nwarps_per_group;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(CTA_THREADS)
 estimator_kernel(const __grid_constant__ Plan plan, const WalkerBuf buf, const int *parent, const Ctl *ctl, double *hist,
                  int nwarps_per_group, size_t group_bytes)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
+  QMC_DYNAMIC_SMEM(smem);
   const Group G = make_group(nwarps_per_group);
   const int groups = (CTA_THREADS / 32) / nwarps_per_group;
   const int g = (threadIdx.x >> 5) / nwarps_per_group;
@@ -301,7 +301,15 @@ estimator_kernel(const __grid_constant__ Plan plan, const WalkerBuf buf, const i
   hist_fx_flush(plan, H.fx, H.base);
 }
 
+#ifdef QMC_EMULATE   /* tests/emu: cudaLaunchKernel gets a trampoline that unpacks the argument array */
+template <int JK, int VK> void prop2_tramp(void **p)
+{
+  propagate_v2_kernel<JK, VK>(*(Plan *)p[0], *(DmcParams *)p[1], *(StepArgs *)p[2], *(double **)p[3], *(int *)p[4], *(size_t *)p[5]);
+}
+template <int JK, int VK> const void *prop2() { return (const void *)&prop2_tramp<JK, VK>; }
+#else
 template <int JK, int VK> const void *prop2() { return (const void *)propagate_v2_kernel<JK, VK>; }
+#endif
 
 const void *prop2_ptr(int ksel)
 {
@@ -344,7 +352,7 @@ cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, cudaStream_t st,
 
 cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int n_partials, int multi_rank)
 {
-  scan_v2_kernel<<<1, SCAN2_THREADS, 0, st>>>(dmc, a, e_old, a.parent, n_partials, multi_rank);
+  QMC_LAUNCH(scan_v2_kernel, 1, SCAN2_THREADS, 0, st, dmc, a, e_old, a.parent, n_partials, multi_rank);
   return cudaGetLastError();
 }
 
@@ -353,7 +361,7 @@ cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan 
 {
   int nw = cfg.nwarps_per_group;
   size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
-  estimator_kernel<<<cfg.grid, cfg.block, cfg.smem, st>>>(plan, buf, parent, ctl, hist, nw, gb);
+  QMC_LAUNCH(estimator_kernel, cfg.grid, cfg.block, cfg.smem, st, plan, buf, parent, ctl, hist, nw, gb);
   return cudaGetLastError();
 }
 
