@@ -37,9 +37,11 @@ struct NcclApi {
   bool load(std::string &err)
   {
     if (h) return true;
-    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    /* QMC4_NCCL_LIB: explicit path of the NCCL to bind (e.g. the torch-bundled one); tried first */
+    const char *names[] = {getenv("QMC4_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char *n : names)
       {
+        if (!n || !*n) continue;
         h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (h) break;
       }

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <mutex>
 #include <cstdio>
 #include <thread>
 #include <vector>
@@ -49,6 +50,7 @@ struct BlockState {
 };
 
 BlockState *g_block = nullptr;
+std::mutex g_launch_mutex;   // one kernel at a time: rank threads of a multi-rank test share the "device"
 thread_local int t_parity = 0;
 
 }  // namespace
@@ -76,6 +78,7 @@ void launch(dim3 grid, dim3 block, size_t smem, void (*body)(void *), void *clos
       std::fprintf(stderr, "emu::launch: block size %u is not a multiple of 32\n", block.x);
       std::abort();
     }
+  std::lock_guard<std::mutex> device(g_launch_mutex);
   std::vector<unsigned char> dyn(smem + 64);
   unsigned char *dyn_aligned = dyn.data() + ((64 - (reinterpret_cast<uintptr_t>(dyn.data()) & 63)) & 63);
   for (unsigned b = 0; b < grid.x; ++b)

@@ -23,7 +23,7 @@ FAST = "not statistical and not population_control and not determinism and not n
 
 @pytest.fixture(scope="module")
 def emu_lib():
-    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR, "all"])
     return EMU_LIB
 
 
@@ -60,6 +60,19 @@ def test_parity_suite_on_emulated_kernels(emu_lib):
     tail = "\n".join(r.stdout.splitlines()[-25:])
     assert r.returncode == 0, tail + r.stderr[-2000:]
     assert " passed" in tail and "failed" not in tail, tail
+
+
+@pytest.mark.parametrize("nranks,N,wpr,wpw", [(2, 16, 24, ""), (4, 40, 10, "2"), (8, 64, 6, "8")])
+def test_multirank_steps_and_rebalance_on_emulated_ranks(emu_lib, nranks, N, wpr, wpw):
+    """ranks = threads over an in-process NCCL stand-in: global E_T / block results identical on every
+    rank, rebalance conserves the walker multiset and equalises the populations (ptools.cpp:93-161)"""
+    env = _env(emu_lib)
+    env["QMC4_NCCL_LIB"] = os.path.join(EMU_DIR, "libnccl_emu.so")
+    if wpw:
+        env["QMC4_WPW"] = wpw
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "multirank_driver.py"), str(nranks), str(N), str(wpr)],
+                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-2000:]
 
 
 @pytest.mark.skipif(os.environ.get("QMC4_TEST_EMULATED_SLOW") != "1", reason="minutes of CPU: set QMC4_TEST_EMULATED_SLOW=1")
