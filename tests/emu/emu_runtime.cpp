@@ -79,7 +79,7 @@ void launch(dim3 grid, dim3 block, size_t smem, void (*body)(void *), void *clos
       std::abort();
     }
   std::lock_guard<std::mutex> device(g_launch_mutex);
-  std::vector<unsigned char> dyn(smem + 64);
+  std::vector<unsigned char> dyn(smem + 64, 0xFF);   /* poison: shared memory starts undefined (NaN as fp64) */
   unsigned char *dyn_aligned = dyn.data() + ((64 - (reinterpret_cast<uintptr_t>(dyn.data()) & 63)) & 63);
   for (unsigned b = 0; b < grid.x; ++b)
     {
@@ -135,7 +135,9 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = emu_sms(); return cudaSuccess; }
 cudaError_t emu_malloc(void **p, size_t n)
 {
-  *p = std::aligned_alloc(256, (n + 255) / 256 * 256 + 256);
+  const size_t bytes = (n + 255) / 256 * 256 + 256;
+  *p = std::aligned_alloc(256, bytes);
+  if (*p) std::memset(*p, 0xFF, bytes);   /* poison: cudaMalloc memory is undefined */
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
