@@ -111,7 +111,12 @@ struct emu_event { std::chrono::steady_clock::time_point t; };
 
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n)
+{ /* QMC4_EMU_DEVICES "GPUs" (all the same host; launches are serialised) for multi-rank tests */
+  const char *s = std::getenv("QMC4_EMU_DEVICES");
+  *n = s ? std::max(1, std::atoi(s)) : 1;
+  return cudaSuccess;
+}
 cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static int emu_sms()

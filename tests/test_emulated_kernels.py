@@ -82,3 +82,55 @@ def test_experimental_pipeline2_bitwise_on_emulated_kernels(emu_lib):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_experimental_pipeline2.py"), "-q",
                         "-m", "gpu", "-p", "no:cacheprovider"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=3000)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def _run_host(tmp_path, cfg, *extra, devices=1):
+    import json
+    with open(os.path.join(tmp_path, "input.json"), "w") as f:
+        json.dump(cfg, f)
+    env = dict(os.environ, QMC4_EMU_DEVICES=str(devices), QMC4_NCCL_LIB=os.path.join(EMU_DIR, "libnccl_emu.so"))
+    return subprocess.run([os.path.join(EMU_DIR, "dmc_b200_emu"), "input.json", *extra], cwd=tmp_path, env=env,
+                          capture_output=True, text=True, timeout=900)
+
+
+def test_host_driver_files_on_emulated_kernels(emu_lib, tmp_path):
+    """dmc_b200 (host C++ over the C ABI) end to end: block report, energy.dat, <label>.dat, checkpoint, restart"""
+    import json
+    import re
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    cfg = cases.dmc_cases()["pbc_N16"]
+    cfg = dict(cfg, nBlocks=3, walkers=24, delta_walkers=3, stepsPerBlock=6)
+    p = _run_host(str(tmp_path), cfg)
+    assert p.returncode == 0, p.stderr
+    out = re.sub(r"\x1b\[[0-9;]*m", "", p.stdout)
+    assert out.count("Block: ") == 3 and "Acc. Ratio: " in out and "totalRunningTime :" in out
+    lines = open(tmp_path / "energy.dat").read().split("\n")
+    assert lines[0] == "energy" and len([x for x in lines[1:] if x.strip()]) == 3
+    assert re.fullmatch(r"-?\d\.\d{12}e[+-]\d\d", lines[1])
+    m = cfg["measurements"][0]
+    blocks = open(tmp_path / (m["label"] + ".dat")).read().strip().split("\n\n")
+    rows = blocks[0].split("\n")
+    assert rows[0] == "x " + m["label"] and len(blocks) == 3 and len(rows) == m["bins"] + 1
+    g = np.array([[float(r.split()[1]) for r in b.split("\n") if not r.startswith("x")] for b in blocks])
+    assert np.isfinite(g).all() and g.sum() > 0
+    ck = json.load(open(tmp_path / "configurations" / "walkers-Rank0.json"))
+    assert sorted(ck["configurations"][0][0]) == ["x", "y", "z"]
+    p2 = _run_host(str(tmp_path), dict(cfg, configurations="configurations", nBlocks=1))
+    assert p2.returncode == 0 and "WARNING" not in p2.stdout
+    pops = [int(x) for x in re.findall(r"Curr. Walkers: (\d+)", re.sub(r"\x1b\[[0-9;]*m", "", p2.stdout))]
+    assert abs(pops[0] - len(ck["configurations"])) <= 0.5 * len(ck["configurations"])
+
+
+def test_host_driver_two_gpu_threads_on_emulated_kernels(emu_lib, tmp_path):
+    """--gpus 2: one host thread per (emulated) GPU, NCCL unique id shared in-process, per-rank checkpoints"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    cfg = dict(cases.dmc_cases()["trap_N10"], nBlocks=3, walkers=40, delta_walkers=4, stepsPerBlock=10)
+    p = _run_host(str(tmp_path), cfg, "--gpus", "2", devices=2)
+    assert p.returncode == 0, p.stderr
+    e = np.loadtxt(tmp_path / "energy.dat", skiprows=1)
+    assert len(e) == 3 and np.isfinite(e).all() and abs(e.mean() - 15.15) < 5
+    assert os.path.exists(tmp_path / "configurations" / "walkers-Rank1.json")
