@@ -125,6 +125,23 @@ int  qmc_add_estimator(qmc_ctx *ctx, int est_kind, const int *sets, int nsets,
                        int bins, double minx, double maxx,
                        const double *extra, int nextra, int *est_index);
 
+/* Forward walking (pure estimators).  Replaces, for the histogram estimator `est_index`:
+ *   storerFactory::create (estimatorsFactory.h:97-131, "recordSteps")  -> realHistogramStorer
+ *     (correlationEstimator.cpp:81-125: the walker's own histogram stored every sampling step in a
+ *      ring of recordSteps entries that follows the walker through branching, walkers.cpp:139-179),
+ *   estimatorFactory::create (estimatorsFactory.cpp:47-74, "forwardWalkingSteps": [..])
+ *     -> one realHistogramForwardWalkingEstimator per entry (correlationEstimator.cpp:128-175): adds,
+ *      for every walker of the current population, the record its ancestor stored fw sampling
+ *      steps earlier, once recordSteps records exist.
+ * The n_fw estimators get the indices *first_index .. *first_index+n_fw-1 (>= QMC_FW_INDEX_BASE) for
+ * qmc_get_estimator.  Must precede qmc_set_dmc.  Errors: vector observables (structure factor) have
+ * no forward-walking estimator in the reference either (missingImplementation, :68);
+ * fw >= recordSteps (assert, correlationEstimator.cpp:137); more than one rank (records do not
+ * migrate yet). */
+#define QMC_FW_INDEX_BASE 65536
+int  qmc_add_forward_walking(qmc_ctx *ctx, int est_index, int record_steps,
+                             const int *fw_steps, int n_fw, int *first_index);
+
 /* dmcDriver constructor arguments + seed + performBranching (dmcDriver.cpp:232-255,
  * main.cpp:363-395).  capacity = walker slots to allocate on this rank (0: 2*(target+delta)/nranks+64).
  * Builds the kernel plan: must follow all qmc_add_* calls. */

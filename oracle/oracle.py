@@ -100,6 +100,21 @@ class _Base:
             self._ck(self._fn("histogram")(txt, tmp.encode(), _dp(R), R.shape[0], iMeas, _dp(sums), bins, C.byref(w)))
         return sums, w.value
 
+    def forward_walking(self, cfg, pops, ancs, iEst, bins):
+        """pops: list of [n_e, dofs] arrays (one per sampling event); ancs: list of int arrays (index into the
+        previous event's population; ancs[0] ignored); iEst: index in the vector estimatorFactory::create returns"""
+        txt = json.dumps(cfg).encode()
+        d = _dofs(cfg)
+        n = np.asarray([len(p) for p in pops], dtype=np.int32)
+        R = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, d) for p in pops]))
+        anc = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.int32) for a in ancs]))
+        assert len(anc) == len(R)
+        sums = np.zeros(bins)
+        w = C.c_double(0)
+        with tempfile.TemporaryDirectory() as tmp:
+            self._ck(self._fn("forward_walking")(txt, tmp.encode(), _dp(R), _ip(n), _ip(anc), len(n), iEst, _dp(sums), bins, C.byref(w)))
+        return sums, w.value
+
     def plan(self, populations):
         p = np.asarray(populations, dtype=np.int32)
         src = np.zeros(len(p), dtype=np.int32)
@@ -278,6 +293,20 @@ class Port(_Base):
         sums = np.zeros(bins)
         w = C.c_double(0)
         self._ck(self.lib.orc_histogram_model(C.byref(m), _dp(R), R.shape[0], iMeas, _dp(sums), bins, C.byref(w)))
+        return sums, w.value
+
+    def forward_walking(self, cfg, pops, ancs, iHist, recordSteps, fwSteps, bins):
+        """iHist: index among the measurements of the input (the target histogram estimator)"""
+        m = self._model(cfg)
+        d = _dofs(cfg)
+        n = np.asarray([len(p) for p in pops], dtype=np.int32)
+        R = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, d) for p in pops]))
+        anc = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.int32) for a in ancs]))
+        assert len(anc) == len(R)
+        sums = np.zeros(bins)
+        w = C.c_double(0)
+        self._ck(self.lib.orc_forward_walking_model(C.byref(m), _dp(R), _ip(n), _ip(anc), len(n), iHist, int(recordSteps),
+                                                    int(fwSteps), _dp(sums), bins, C.byref(w)))
         return sums, w.value
 
     def plan(self, populations):

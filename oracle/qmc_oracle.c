@@ -811,6 +811,79 @@ int orc_histogram_model(const orc_model *m, const double *R, int nW, int iEst, d
   return 0;
 }
 
+/* ---- forward walking (dmc/correlationEstimator.cpp) ----------------------------------------------
+ * Restatement over a given genealogy (same arguments as ref_forward_walking in ref_shim.cpp).
+ * Per walker: a ring data[recordSteps][bins], a time index and a filling flag
+ * (realHistogramStorer::reserve, :109-115).  Every sampling event each walker first stores its own
+ * histogram, sums/weight with weight 1 (store, :87-107), then the estimator adds the record
+ * wrapIndex(i - forwardWalkingSteps - 1) of every walker whose ring has wrapped (accumulate, :128-152;
+ * wrapIndex: tools.cpp:163-166).  Cloning copies the whole walker (walkers.cpp:139-179). */
+typedef struct { double *data; int i, filling; } fw_walker;
+
+int orc_forward_walking_model(const orc_model *m, const double *R, const int *n, const int *anc, int K, int iEst,
+                              int recordSteps, int fwSteps, double *sums, int bins, double *weight)
+{
+  int dofs = 0;
+  for (int s = 0; s < m->nSpecies; s++) dofs += 3 * m->N[s];
+  if (fwSteps >= recordSteps) return fail("forwardWalkingSteps < recordSteps (assert, correlationEstimator.cpp:137)");
+  for (int b = 0; b < bins; b++) sums[b] = 0;
+  *weight = 0;
+  fw_walker *pop = NULL, *next = NULL;
+  int npop = 0, rc = 0;
+  size_t off = 0;
+  const size_t ring = (size_t)recordSteps * bins;
+  double *tmp = malloc(sizeof(double) * bins);
+  for (int e = 0; e < K && !rc; e++)
+    {
+      next = malloc(sizeof(fw_walker) * (n[e] > 0 ? n[e] : 1));
+      for (int i = 0; i < n[e]; i++)
+        {
+          next[i].data = malloc(sizeof(double) * ring);
+          if (e == 0)
+            {
+              for (size_t k = 0; k < ring; k++) next[i].data[k] = 0;
+              next[i].i = 0;
+              next[i].filling = 1;
+            }
+          else
+            {
+              const fw_walker *src = pop + anc[off + i];
+              memcpy(next[i].data, src->data, sizeof(double) * ring);
+              next[i].i = src->i;
+              next[i].filling = src->filling;
+            }
+        }
+      for (int i = 0; i < n[e] && !rc; i++)
+        {
+          fw_walker *w = next + i;
+          double wt = 0;
+          rc = orc_histogram_model(m, R + (off + i) * dofs, 1, iEst, tmp, bins, &wt);      /* tmpAcc.clear(); ob->accumulate(w,psi,tmpAcc) */
+          if (rc) break;
+          for (int j = 0; j < bins; j++) w->data[(size_t)w->i * bins + j] = tmp[j] / wt;
+          w->i = (w->i + 1) % recordSteps;
+          if (w->i == 0) w->filling = 0;
+          {
+            int t = w->i - fwSteps - 1;
+            int j = (t >= 0) ? t % recordSteps : recordSteps + t;
+            if (!w->filling)
+              {
+                for (int b = 0; b < bins; b++) sums[b] += w->data[(size_t)j * bins + b];
+                *weight += 1;
+              }
+          }
+        }
+      for (int i = 0; i < npop; i++) free(pop[i].data);
+      free(pop);
+      pop = next;
+      npop = n[e];
+      off += n[e];
+    }
+  for (int i = 0; i < npop; i++) free(pop[i].data);
+  free(pop);
+  free(tmp);
+  return rc;
+}
+
 /* ---- branching (dmc/branching.cpp) ---------------------------------------------------------------- */
 double orc_energy_shift(const double *E, int n, double timeStep, double meanWalkers_, double deltaWalkers_)
 { /* setEnergyShift (branching.cpp:65-97); meanWalkers/deltaWalkers are size_t members (branching.h:23-24) */

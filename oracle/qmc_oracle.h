@@ -47,6 +47,8 @@ int orc_green_ratio_model(const orc_model *m, double timeStep, int nW, const dou
 int orc_drift_diffuse_model(const orc_model *m, double timeStep, int nW, const double *Rold, const double *Fold,
                             const double *xi_draw_order, double *Rnew);
 int orc_histogram_model(const orc_model *m, const double *R, int nW, int iEst, double *sums, int bins, double *weight);
+int orc_forward_walking_model(const orc_model *m, const double *R, const int *n, const int *anc, int K, int iEst,
+                              int recordSteps, int fwSteps, double *sums, int bins, double *weight);
 
 /* branchingControl (dmc/branching.cpp) with the uniforms supplied by the caller */
 double orc_energy_shift(const double *E, int n, double timeStep, double meanWalkers, double deltaWalkers);

@@ -44,6 +44,7 @@
 #include "trimerCorrelation.h"
 #include "potentialFunctors.h"
 #include "estimatorCollection.h"
+#include "correlationEstimator.h"
 
 #include <sstream>
 #include <string>
@@ -272,6 +273,74 @@ int ref_histogram(const char * jsonText, const char * scratchDir, const double *
           }
         auto * h = dynamic_cast<realHistogramEstimator*>(coll[iMeas].get());
         if (!h) throw std::runtime_error("measurement is not a histogram estimator");
+        auto & acc = h->getAccumulator();
+        if ((int)acc.size() != bins) throw std::runtime_error("bins mismatch");
+        for (int i = 0; i < bins; i++) sums[i] = acc.sums()(i);
+        *weight = acc.weight();
+      }
+    catch (...) { if (chdir(cwd) != 0) {} throw; }
+    if (chdir(cwd) != 0) throw std::runtime_error("chdir back");
+  });
+}
+
+/* Forward walking through the reference's own classes over a GIVEN genealogy: K sampling events;
+ * event e has n[e] walkers with configurations R (events concatenated) and anc[i] = index, in the
+ * population of event e-1, of the walker this one descends from (ignored for e = 0).  Walkers are
+ * copied the way branching copies them (whole dmcWalker, so the record rings follow:
+ * walkers.cpp:139-179), then estimatorCollection::accumulate runs the storers
+ * (realHistogramStorer::store, correlationEstimator.cpp:87-107) and the estimators
+ * (realHistogramForwardWalkingEstimator::accumulate, :128-152) exactly as dmcDriver::accumulate does.
+ * iEst indexes the vector estimatorFactory::create returns for j["measurements"]. */
+int ref_forward_walking(const char * jsonText, const char * scratchDir, const double * R, const int * n,
+                        const int * anc, int K, int iEst, double * sums, int bins, double * weight)
+{
+  return guarded([&] {
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof cwd)) throw std::runtime_error("getcwd");
+    if (chdir(scratchDir) != 0) throw std::runtime_error("chdir scratch");
+    try
+      {
+        model m(jsonText);
+        auto ests = getFactory().createEstimators(m.j["measurements"]);
+        auto storers = getFactory().createStorers(m.j["measurements"]);
+        estimatorCollection coll;
+        for (auto * st : storers) coll.push_back(st);      /* main.cpp:411-420: storers, then estimators */
+        for (auto * e : ests) coll.push_back(e);
+        /* histogramAccumulator's default constructor leaves _weight uninitialised (accumulators.h:104) and
+           realHistogramForwardWalkingEstimator only resizes it (correlationEstimator.cpp:156-158): the weight of the
+           FIRST block of a reference run is garbage + count.  Every later block starts from
+           estimatorCollection::clear() (dmcDriver.cpp:225) — that defined behaviour is what we pin. */
+        coll.clear();
+        std::vector<dmcWalker> pop, next;
+        size_t off = 0;
+        for (int e = 0; e < K; e++)
+          {
+            next.clear();
+            next.reserve(n[e]);
+            for (int i = 0; i < n[e]; i++)
+              {
+                if (e == 0)
+                  {
+                    dmcWalker wk;
+                    wk.getStates() = m.unpack(R + (off + i) * m.dofs);
+                    initializer::registerDistances(wk.getTableDistances(), *m.psi);
+                    initializer::addDistances(wk, coll);
+                    coll.reserve(wk);
+                    next.push_back(wk);
+                  }
+                else
+                  {
+                    next.push_back(pop.at(anc[off + i]));
+                    next.back().getStates() = m.unpack(R + (off + i) * m.dofs);
+                  }
+                if (!updateForceGradientEnergy(next.back(), *m.psi, *m.eO)) throw std::runtime_error("invalid configuration");
+              }
+            for (auto & wk : next) coll.accumulate(wk, *m.psi);
+            pop.swap(next);
+            off += n[e];
+          }
+        auto * h = dynamic_cast<realHistogramForwardWalkingEstimator*>(coll[iEst].get());
+        if (!h) throw std::runtime_error("measurement is not a forward-walking histogram estimator");
         auto & acc = h->getAccumulator();
         if ((int)acc.size() != bins) throw std::runtime_error("bins mismatch");
         for (int i = 0; i < bins; i++) sums[i] = acc.sums()(i);

@@ -136,6 +136,19 @@ struct qmc_ctx {
   cudaEvent_t ev_scan = nullptr, ev_ar = nullptr;
   bool ar_pending = false;
   double *e_old = nullptr;
+  // forward walking (kernels_fw.cu; correlationEstimator.cpp): ring of per-slot histogram rows + ancestor links
+  struct FwEst { int target, fw, record_steps; double *sums = nullptr, *weight = nullptr; };
+  std::vector<FwEst> fw_est;
+  int max_sf_bins = 0;
+  int fw_depth = 0;                 // events kept = max(fw)+1
+  long fw_event = 0;                // sampling events since the last upload
+  double *fw_rows = nullptr;        // [depth][cap][hist_stride]
+  int *fw_links = nullptr;          // [depth][cap]  slot at event e -> ancestor slot at event e-1
+  int *fw_comp[2] = {nullptr, nullptr};
+  int fw_comp_cur = 0;
+  int *fw_cnt = nullptr, *fw_nslots = nullptr;
+  double *fw_partial = nullptr;
+  size_t fw_group_bytes = 0;
 };
 
 namespace {
@@ -541,6 +554,7 @@ int build_plan(qmc_ctx *c)
     }
   P.needs_pair_table = tab;
   P.aux_doubles = max_sf_bins * 2 * wpw;
+  c->max_sf_bins = max_sf_bins;
   size_t group_doubles = (size_t)P.dofs * (1 + wpw) + (wpw * 4 + 8) + tab + P.aux_doubles;
   group_doubles = (group_doubles + 1) & ~(size_t)1;
   c->cfg.block = 256;
@@ -639,6 +653,45 @@ int sync_all(qmc_ctx *c)
   return 0;
 }
 
+// Forward walking bookkeeping after the scan of a step (kernels_fw.cu).  c->parent is the parent map of the
+// NEXT step (post-branching walker -> slot of the buffer just written), c->n_desc the descendants per slot.
+int fw_after_step(qmc_ctx *c, int sample)
+{
+  const int cap = (int)c->cap, D = c->fw_depth, stride = c->plan.hist_stride;
+  const int g = std::max(1, std::min(c->sms * 4, (cap + 255) / 256));
+  if (!sample)
+    { /* between sampling events the ancestor map is composed with every step's parent map */
+      CK(launch_fw_compose(c->stream, g, c->parent, c->fw_comp[c->fw_comp_cur], c->fw_comp[c->fw_comp_cur ^ 1], c->ctl, 0));
+      c->fw_comp_cur ^= 1;
+      c->launches += 1;
+      return 0;
+    }
+  const long e = c->fw_event;
+  const int slot = (int)(e % D);
+  if (e > 0)
+    {
+      CK(launch_fw_copy_links(c->stream, g, c->fw_comp[c->fw_comp_cur], c->fw_links + (size_t)slot * cap, c->ctl));
+      c->launches += 1;
+    }
+  CK(launch_fw_record(c->stream, std::max(1, std::min(cap, c->sms * 2)), c->fw_group_bytes, c->plan, c->buf[c->cur], c->n_desc, c->ctl,
+                      c->fw_rows + (size_t)slot * cap * stride, c->fw_nslots + slot));
+  c->launches += 1;
+  for (auto &f : c->fw_est)
+    {
+      if (e + 1 < f.record_steps) continue;     /* the walkers' rings are still filling (correlationEstimator.cpp:143) */
+      const int tslot = (int)((e - f.fw) % D);
+      const Estimator &E = c->plan.est[f.target];
+      CK(launch_fw_accumulate(c->stream, g, c->parent, c->fw_links, D, cap, e, f.fw, c->ctl, c->fw_cnt,
+                              c->fw_rows + (size_t)tslot * cap * stride, c->fw_nslots + tslot, stride, E.offset, E.bins, c->fw_partial,
+                              f.sums, f.weight));
+      c->launches += 3;
+    }
+  CK(launch_fw_compose(c->stream, g, c->parent, nullptr, c->fw_comp[c->fw_comp_cur], c->ctl, 1));
+  c->launches += 1;
+  c->fw_event = e + 1;
+  return 0;
+}
+
 int one_step_v2(qmc_ctx *c, int accumulate)
 { /* propagate(k) || all-reduce(k-1)  ->  scan(k)  ->  { all-reduce(k) on the comm stream } || estimators(k) || propagate(k+1) */
   StepArgs a = make_step_args(c, accumulate);
@@ -680,7 +733,8 @@ int one_step(qmc_ctx *c, int accumulate, const TraceDev *tr)
   CK(launch_scan(c->stream, c->dmc, a, c->n_partials, c->nranks > 1, 0));
   c->launches += 2;
   c->cur ^= 1;
-  return allreduce_sums(c);
+  if (allreduce_sums(c)) return 1;
+  return c->fw_est.empty() ? 0 : fw_after_step(c, accumulate);
 }
 
 } // namespace
@@ -810,6 +864,18 @@ void qmc_destroy(qmc_ctx *c)
   cudaFree(c->scr_i);
   cudaFree(c->slab_send);
   cudaFree(c->slab_recv);
+  cudaFree(c->fw_rows);
+  cudaFree(c->fw_links);
+  cudaFree(c->fw_comp[0]);
+  cudaFree(c->fw_comp[1]);
+  cudaFree(c->fw_cnt);
+  cudaFree(c->fw_nslots);
+  cudaFree(c->fw_partial);
+  for (auto &f : c->fw_est)
+    {
+      cudaFree(f.sums);
+      cudaFree(f.weight);
+    }
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (int i = 0; i < qmc_ctx::NEV; ++i)
     {
@@ -875,11 +941,39 @@ int qmc_add_estimator(qmc_ctx *c, int est_kind, const int *sets, int nsets, int 
   return 0;
 }
 
+int qmc_add_forward_walking(qmc_ctx *c, int est_index, int record_steps, const int *fw_steps, int n_fw, int *first_index)
+{
+  if (!c) return 1;
+  if (c->planned) return fail(c, "forward walking must be declared before qmc_set_dmc");
+  if (est_index < 0 || est_index >= (int)c->est.size()) return fail(c, "forward walking: estimator index out of range");
+  const int kind = c->est[est_index].kind;
+  if (kind != QMC_EST_PAIRCORRELATION && kind != QMC_EST_TRIMERCORRELATION_UNDIS)
+    /* estimatorsFactory.cpp:66-69: only scalar and histogram observables have forward-walking estimators */
+    return fail(c, "Forward walking estimator for vector not yet implemented");
+  if (record_steps < 1 || n_fw < 1 || !fw_steps) return fail(c, "forward walking: recordSteps and forwardWalkingSteps are required");
+  for (int k = 0; k < n_fw; ++k)
+    if (fw_steps[k] < 0 || fw_steps[k] >= record_steps)
+      return fail(c, "forward walking: forwardWalkingSteps must be in [0, recordSteps)");   /* assert, correlationEstimator.cpp:137 */
+  if (first_index) *first_index = QMC_FW_INDEX_BASE + (int)c->fw_est.size();
+  for (int k = 0; k < n_fw; ++k)
+    {
+      qmc_ctx::FwEst f;
+      f.target = est_index;
+      f.fw = fw_steps[k];
+      f.record_steps = record_steps;
+      c->fw_est.push_back(f);
+    }
+  return 0;
+}
+
 int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t deltaWalkers, uint64_t seed,
                 int branching_on, int64_t capacity)
 {
   if (!c) return 1;
   if (c->planned) return fail(c, "qmc_set_dmc called twice");
+  if (!c->fw_est.empty() && c->nranks > 1)
+    return fail(c, "forward walking runs on one GPU in this build: walker records do not migrate between ranks yet");
+  if (!c->fw_est.empty()) c->pipeline = 1;
   if (!c->planning_only) cudaSetDevice(c->device);
   if (build_plan(c)) return 1;
   DmcParams &D = c->dmc;
@@ -929,6 +1023,39 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
       CK(cudaMalloc(&c->hist, (size_t)c->cfg.grid * c->plan.hist_stride * 8));
       CK(cudaMemset(c->hist, 0, (size_t)c->cfg.grid * c->plan.hist_stride * 8));
       CK(cudaMalloc(&c->hist_out, (size_t)c->plan.hist_stride * 8));
+    }
+  if (!c->fw_est.empty())
+    {
+      int maxfw = 0, maxbins = 1;
+      for (auto &f : c->fw_est)
+        {
+          maxfw = std::max(maxfw, f.fw);
+          maxbins = std::max(maxbins, c->plan.est[f.target].bins);
+        }
+      c->fw_depth = maxfw + 1;
+      CK(configure_kernels_fw(c->max_smem));
+      c->fw_group_bytes = fw_record_group_bytes(c->plan, c->max_sf_bins);
+      if (c->fw_group_bytes + (size_t)c->plan.hist_stride * 8 > (size_t)c->max_smem)
+        return fail(c, "forward walking: the record kernel needs more shared memory than one CTA has for this system size");
+      const size_t ring = (size_t)c->fw_depth * capacity * c->plan.hist_stride * 8;
+      if (cudaMalloc(&c->fw_rows, ring) != cudaSuccess)
+        return fail(c, "forward walking: cannot allocate the record ring (" + std::to_string(ring >> 20) +
+                           " MiB = (max forwardWalkingSteps+1) x capacity x bins x 8 B): fewer walkers, bins or forward-walking steps");
+      CK(cudaMalloc(&c->fw_links, (size_t)c->fw_depth * capacity * 4));
+      CK(cudaMalloc(&c->fw_comp[0], capacity * 4));
+      CK(cudaMalloc(&c->fw_comp[1], capacity * 4));
+      CK(cudaMalloc(&c->fw_cnt, capacity * 4));
+      CK(cudaMalloc(&c->fw_nslots, (size_t)c->fw_depth * 4));
+      CK(cudaMemset(c->fw_nslots, 0, (size_t)c->fw_depth * 4));
+      CK(cudaMalloc(&c->fw_partial, (size_t)fw_chunks() * maxbins * 8));
+      for (auto &f : c->fw_est)
+        {
+          const int bins = c->plan.est[f.target].bins;
+          CK(cudaMalloc(&f.sums, (size_t)bins * 8));
+          CK(cudaMalloc(&f.weight, 8));
+          CK(cudaMemset(f.sums, 0, (size_t)bins * 8));
+          CK(cudaMemset(f.weight, 0, 8));
+        }
     }
   c->planned = true;
   return 0;
@@ -1026,6 +1153,7 @@ int qmc_upload_walkers(qmc_ctx *c, const double *R, int64_t nW)
   cudaSetDevice(c->device);
   if (nW < 1) return fail(c, "need at least one walker");
   if (nW > c->cap) return fail(c, "more walkers than capacity");
+  c->fw_event = 0;                     /* a new population starts with empty records (storer::reserve) */
   const size_t dofs = c->plan.dofs;
   WalkerBuf &B = c->buf[c->cur];
   CK(cudaMemcpyAsync(B.R, R, nW * dofs * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1203,6 +1331,20 @@ int qmc_get_estimator(qmc_ctx *c, int est_index, double *sums, int bins, double 
   if (!c) return 1;
   if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
   if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
+  if (est_index >= QMC_FW_INDEX_BASE)
+    { /* forward-walking estimator: sums and weight of realHistogramForwardWalkingEstimator */
+      const int k = est_index - QMC_FW_INDEX_BASE;
+      if (k >= (int)c->fw_est.size()) return fail(c, "estimator index out of range");
+      const auto &f = c->fw_est[k];
+      if (bins != c->plan.est[f.target].bins) return fail(c, "bins mismatch");
+      cudaSetDevice(c->device);
+      double w = 0;
+      CK(cudaMemcpyAsync(sums, f.sums, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(&w, f.weight, 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (weight) *weight = w;
+      return 0;
+    }
   if (est_index < 0 || est_index >= c->plan.nest) return fail(c, "estimator index out of range");
   if (c->pipeline == 2 && sync_all(c)) return 1;
   const Estimator &E = c->plan.est[est_index];
@@ -1239,6 +1381,11 @@ int qmc_clear_estimators(qmc_ctx *c)
   cudaSetDevice(c->device);
   if (c->hist) CK(cudaMemsetAsync(c->hist, 0, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8, c->stream));
   CK(cudaMemsetAsync(&c->ctl->est_weight, 0, 8, c->stream));
+  for (auto &f : c->fw_est)
+    { /* accumulators are cleared every block (estimatorCollection::clear); the walkers' rings are not */
+      CK(cudaMemsetAsync(f.sums, 0, (size_t)c->plan.est[f.target].bins * 8, c->stream));
+      CK(cudaMemsetAsync(f.weight, 0, 8, c->stream));
+    }
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1473,6 +1620,9 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "n_triplet_passes") *value = c->plan.n3b;
   else if (k == "n_estimators") *value = c->plan.nest;
   else if (k == "hist_stride") *value = c->plan.hist_stride;
+  else if (k == "fw_events") *value = (double)c->fw_event;
+  else if (k == "fw_depth") *value = c->fw_depth;
+  else if (k == "fw_ring_bytes") *value = (double)c->fw_depth * (double)c->cap * c->plan.hist_stride * 8.0;
   else if (k == "groups_per_cta") *value = c->cfg.groups_per_cta;
   else if (k == "log_up") *value = c->dmc.log_up;
   else if (k == "log_down") *value = c->dmc.log_down;

@@ -105,4 +105,16 @@ cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs
 cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const WalkerBuf &buf, const int *parent,
                               const Ctl *ctl, double *hist);
 
+// forward walking (kernels_fw.cu)
+size_t fw_record_group_bytes(const Plan &plan, int max_sf_bins);
+cudaError_t configure_kernels_fw(int max_smem_optin);
+int fw_chunks();
+cudaError_t launch_fw_record(cudaStream_t st, int grid, size_t group_bytes, const Plan &plan, const WalkerBuf &buf, const int *n_desc,
+                             const Ctl *ctl, double *rows, int *nslots_out);
+cudaError_t launch_fw_compose(cudaStream_t st, int grid, const int *parent, const int *comp_in, int *comp_out, const Ctl *ctl, int fresh);
+cudaError_t launch_fw_copy_links(cudaStream_t st, int grid, const int *comp, int *link, const Ctl *ctl);
+cudaError_t launch_fw_accumulate(cudaStream_t st, int grid, const int *parent, const int *links, int depth, int cap, long event, int fw,
+                                 const Ctl *ctl, int *cnt, const double *rows, const int *nslots, int stride, int offset, int bins,
+                                 double *partial, double *sums, double *weight);
+
 } // namespace qmc

@@ -127,6 +127,30 @@ void realHistogramEstimator::write(std::ostream &stream)
   for (size_t i = 0; i < x.size(); i++) stream << x[i] << " " << sums[i] / weight << std::endl;
 }
 
+void forwardWalkingGroup::ensureRegistered(qmc_ctx *ctx)
+{
+  if (first >= 0) return;
+  const int target = ob->emit(ctx, bins, minx, maxx);
+  rethrow(ctx, qmc_add_forward_walking(ctx, target, recordSteps, steps.data(), (int)steps.size(), &first));
+}
+realHistogramForwardWalkingEstimator::realHistogramForwardWalkingEstimator(std::shared_ptr<forwardWalkingGroup> g, int k_,
+                                                                           const std::string &label)
+    : estimatorBase(label), group(g), k(k_)
+{
+  sums.assign(group->bins, 0);
+  headerIfEmpty("x " + _label);                       /* correlationEstimator.cpp:160-168 */
+}
+void realHistogramForwardWalkingEstimator::collect(qmc_ctx *ctx, const qmc_block_result &)
+{
+  rethrow(ctx, qmc_get_estimator(ctx, group->first + k, sums.data(), (int)sums.size(), &weight));
+}
+void realHistogramForwardWalkingEstimator::write(std::ostream &stream)
+{ /* correlationEstimator.cpp:171-178 -> histogramAccumulator::writeAverage (accumulators.h:146-156): bin CENTRES */
+  if (!(weight > 0)) return;
+  const real_t dx = (group->maxx - group->minx) / group->bins;
+  for (size_t i = 0; i < sums.size(); i++) stream << group->minx + (i + 0.5) * dx << " " << sums[i] / weight << std::endl;
+}
+
 // ---- factory ---------------------------------------------------------------------------------------------
 factory &getFactory()
 {
@@ -183,7 +207,25 @@ std::vector<estimatorBase *> factory::createEstimators(const json_t &j)
   for (const json_t &e : j.elements())
     {
       const std::string id = e["kind"].get<std::string>();
-      if (e.contains("forwardWalkingSteps")) throw missingImplementation("Forward walking estimators are not on the GPU path yet");
+      if (e.contains("forwardWalkingSteps"))
+        { /* estimatorsFactory.cpp:47-74 */
+          auto it = obs.find(id);
+          if (it == obs.end()) throw factoryIdNotRecorded(id);
+          auto g = std::make_shared<forwardWalkingGroup>();
+          g->ob.reset(it->second(e));
+          if (g->ob->isVector()) throw missingImplementation("Forward walking estimator for vector not yet implemented");
+          if (!e.contains("recordSteps") || e["recordSteps"].get<int>() <= 0)
+            throw invalidInput("forwardWalkingSteps needs recordSteps > 0 on the same measurement (the storer, estimatorsFactory.h:112-121)");
+          g->bins = e["bins"].get<int>();
+          g->minx = e["minx"].get<real_t>();
+          g->maxx = e["maxx"].get<real_t>();
+          g->recordSteps = e["recordSteps"].get<int>();
+          for (const json_t &st : e["forwardWalkingSteps"].elements()) g->steps.push_back(st.get<int>());
+          const std::string label = e["label"].get<std::string>();
+          for (size_t k = 0; k < g->steps.size(); k++)
+            out.push_back(new realHistogramForwardWalkingEstimator(g, (int)k, label + "_fw" + std::to_string(g->steps[k])));
+          continue;
+        }
       if (id == "superfluidFraction") throw missingImplementation("superfluidFraction is not on the GPU path yet");
       if (id == "forceEnergy" || id == "energy") continue;
       auto it = obs.find(id);

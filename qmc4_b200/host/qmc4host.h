@@ -347,6 +347,32 @@ class realHistogramEstimator : public estimatorBase {           // estimators.cp
   bool vectorStyle;
 };
 
+// Forward walking (correlationEstimator.h:129-145, estimatorsFactory.cpp:47-74): a measurement with
+// "forwardWalkingSteps": [..] yields one estimator "<label>_fw<steps>" per entry instead of the plain one,
+// fed by the storer that "recordSteps" creates (estimatorsFactory.h:97-131).  On the device the storer is
+// the record ring of qmc_add_forward_walking; the siblings of one measurement share its registration.
+struct forwardWalkingGroup {
+  std::unique_ptr<observableBase> ob;
+  int bins = 0, recordSteps = 0, first = -1;
+  real_t minx = 0, maxx = 0;
+  std::vector<int> steps;
+  void ensureRegistered(qmc_ctx *ctx);
+};
+class realHistogramForwardWalkingEstimator : public estimatorBase {
+ public:
+  realHistogramForwardWalkingEstimator(std::shared_ptr<forwardWalkingGroup> group, int k, const std::string &label);
+  void registerOn(qmc_ctx *ctx) override { group->ensureRegistered(ctx); }
+  void collect(qmc_ctx *ctx, const qmc_block_result &) override;
+  void write(std::ostream &stream) override;
+  std::vector<int> sets() const override { return {}; }
+
+ private:
+  std::shared_ptr<forwardWalkingGroup> group;
+  int k;
+  std::vector<real_t> sums;
+  real_t weight = 0;
+};
+
 // ---- factory (dmc/factory.h) -------------------------------------------------------------------------
 class factory {
  public:

@@ -94,6 +94,7 @@ class System:
         if rc:
             raise RuntimeError(self.lib.qmc_last_error(None).decode())
         self.estimators = []   # (label, kind, bins, minx, maxx)
+        self.hidden_estimators = []   # targets of forward-walking estimators (not reported, estimatorsFactory.cpp:47)
         self.rank, self.nranks = 0, 1
 
     # -- error plumbing ---------------------------------------------------------------------
@@ -160,8 +161,22 @@ class System:
                                                 0.0, 0.0, _dp(extra), 3, C.byref(idx)))
         else:
             raise factoryIdNotRecorded(kind)
-        self.estimators.append(dict(label=jm.get("label", kind), kind=kind, bins=int(jm["bins"]), index=idx.value,
-                                    minx=float(jm.get("minx", 0.0)), maxx=float(jm.get("maxx", 0.0))))
+        plain = dict(label=jm.get("label", kind), kind=kind, bins=int(jm["bins"]), index=idx.value,
+                     minx=float(jm.get("minx", 0.0)), maxx=float(jm.get("maxx", 0.0)))
+        if "forwardWalkingSteps" in jm:
+            # estimatorsFactory.cpp:47-74: one forward-walking estimator "<label>_fw<steps>" per entry INSTEAD of
+            # the plain one; the storer exists when recordSteps > 0 (estimatorsFactory.h:112-121)
+            fw = np.asarray([int(x) for x in jm["forwardWalkingSteps"]], dtype=np.int32)
+            first = C.c_int(-1)
+            self._ck(self.lib.qmc_add_forward_walking(self.ctx, idx.value, int(_get(jm, "recordSteps")), _ip(fw), len(fw),
+                                                      C.byref(first)))
+            plain["hidden"] = True                 # still accumulated on the device, not reported by the reference
+            self.hidden_estimators.append(plain)
+            for k, steps in enumerate(fw):
+                self.estimators.append(dict(plain, label="%s_fw%d" % (plain["label"], steps), index=first.value + k,
+                                            forwardWalkingSteps=int(steps), targetLabel=plain["label"], hidden=False))
+            return idx.value
+        self.estimators.append(plain)
         return idx.value
 
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
@@ -257,7 +272,7 @@ class System:
         return {f: getattr(r, f) for f, _ in capi.BlockResult._fields_}
 
     def estimator(self, index):
-        e = [x for x in self.estimators if x["index"] == index][0]
+        e = [x for x in self.estimators + self.hidden_estimators if x["index"] == index][0]
         sums = np.zeros(e["bins"])
         w = C.c_double(0)
         self._ck(self.lib.qmc_get_estimator(self.ctx, index, _dp(sums), e["bins"], C.byref(w)))

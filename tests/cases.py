@@ -105,3 +105,51 @@ def dmc_cases():
     p = pbc(16, 2.6, walkers=400, meas=[{"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": 26, "minx": 0, "maxx": 1.3}])
     p.update(timeStep=5e-3, stepsPerBlock=200, nBlocks=160, seed=77)
     return {"trap_N10": t, "pbc_N16": p}
+
+
+def forward_walking_cases():
+    """Small systems with a stored histogram estimator ("recordSteps") and forward-walking estimators
+    ("forwardWalkingSteps": [..], estimatorsFactory.cpp:47-74).  name -> cfg."""
+    fw = {"recordSteps": 4, "forwardWalkingSteps": [0, 1, 3]}
+    p = pbc(8, 2.2, walkers=24, meas=[dict({"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": 16, "minx": 0.0, "maxx": 1.1}, **fw)])
+    p.update(timeStep=2e-2, delta_walkers=3, seed=11)
+    t = three_body(N=7, L=3.0)
+    t.update(timeStep=2e-2, walkers=20, delta_walkers=3)
+    t["measurements"] = [dict({"kind": "trimerCorrelationUnDis", "label": "trimer", "sets": [0], "bins": 12, "minx": 0.0, "maxx": 1.5},
+                              recordSteps=3, forwardWalkingSteps=[2, 0])]
+    m = mixture()
+    m.update(N=[4, 5], lBox=[3.0, 3.0, 3.0], timeStep=1e-2, walkers=18, delta_walkers=3)
+    m["measurements"] = [{"kind": "pairCorrelation", "label": "g00", "sets": [0, 0], "bins": 9, "minx": 0.1, "maxx": 1.5},
+                         dict({"kind": "pairCorrelation", "label": "g01", "sets": [0, 1], "bins": 10, "minx": 0.0, "maxx": 1.5},
+                              recordSteps=5, forwardWalkingSteps=[4, 2])]
+    return {"pbc_pair": p, "three_body_trimer": t, "mixture_g01": m}
+
+
+def fw_measurement(cfg):
+    """(index among the measurements, measurement dict) of the forward-walking measurement of a case"""
+    for i, m in enumerate(cfg["measurements"]):
+        if "forwardWalkingSteps" in m:
+            return i, m
+    raise KeyError("no forward-walking measurement")
+
+
+def synthetic_genealogy(cfg, K, n0, seed):
+    """K sampling events of random configurations with random cloning/killing between them"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    L = np.asarray(cfg["lBox"], dtype=float)
+    pops, ancs = [], []
+    n = n0
+    for e in range(K):
+        if e == 0:
+            anc = np.arange(n)
+        else:
+            nprev = len(pops[-1])
+            n = max(2, nprev + int(rng.integers(-2, 3)))
+            anc = np.sort(rng.integers(0, nprev, size=n))
+        cols = []
+        for N in cfg["N"]:
+            cols.append((rng.uniform(-0.5, 0.5, size=(n, 3, N)) * L[None, :, None]).reshape(n, -1))
+        pops.append(np.concatenate(cols, axis=1))
+        ancs.append(anc.astype(np.int32))
+    return pops, ancs

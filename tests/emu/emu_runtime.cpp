@@ -81,8 +81,9 @@ void launch(dim3 grid, dim3 block, size_t smem, void (*body)(void *), void *clos
   std::lock_guard<std::mutex> device(g_launch_mutex);
   std::vector<unsigned char> dyn(smem + 64, 0xFF);   /* poison: shared memory starts undefined (NaN as fp64) */
   unsigned char *dyn_aligned = dyn.data() + ((64 - (reinterpret_cast<uintptr_t>(dyn.data()) & 63)) & 63);
-  for (unsigned b = 0; b < grid.x; ++b)
+  for (unsigned lin = 0; lin < grid.x * grid.y; ++lin)
     {
+      const unsigned b = lin % grid.x, by = lin / grid.x;
       BlockState bs;
       bs.warps = std::vector<WarpState>(block.x / 32);
       g_block = &bs;
@@ -91,7 +92,7 @@ void launch(dim3 grid, dim3 block, size_t smem, void (*body)(void *), void *clos
       for (unsigned t = 0; t < block.x; ++t)
         th.emplace_back([=]() {
           tls.tid = uint3{t, 0, 0};
-          tls.bid = uint3{b, 0, 0};
+          tls.bid = uint3{b, by, 0};
           tls.bdim = block;
           tls.gdim = grid;
           tls.dyn_smem = dyn_aligned;

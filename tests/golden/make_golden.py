@@ -71,6 +71,22 @@ def main():
     pieces["plan/pops"], pieces["plan/sources"], pieces["plan/amounts"] = pops, np.stack(srcs), np.stack(amts)
     np.savez_compressed(os.path.join(HERE, "pieces.npz"), **pieces)
 
+    # forward walking: the reference's storer + forward-walking estimator classes over synthetic genealogies
+    fwd = {}
+    for name, cfg in cases.forward_walking_cases().items():
+        iM, meas = cases.fw_measurement(cfg)
+        pops, ancs = cases.synthetic_genealogy(cfg, 9, 6, 1000 + len(name))
+        fwd[name + "/n"] = np.asarray([len(p_) for p_ in pops])
+        fwd[name + "/R"] = np.concatenate(pops)
+        fwd[name + "/anc"] = np.concatenate(ancs)
+        # index in the vector estimatorFactory::create returns: plain estimators before it count one each
+        first = sum(len(m_.get("forwardWalkingSteps", [0])) if "forwardWalkingSteps" in m_ else 1 for m_ in cfg["measurements"][:iM])
+        for k, steps in enumerate(meas["forwardWalkingSteps"]):
+            sums, w = ref.forward_walking(cfg, pops, ancs, first + k, meas["bins"])
+            fwd["%s/fw%d/sums" % (name, steps)] = sums
+            fwd["%s/fw%d/weight" % (name, steps)] = np.asarray(w)
+    np.savez_compressed(os.path.join(HERE, "forward_walking.npz"), **fwd)
+
     if "--dmc" in sys.argv:
         res = {}
         for name, cfg in cases.dmc_cases().items():

@@ -134,3 +134,11 @@ def test_host_driver_two_gpu_threads_on_emulated_kernels(emu_lib, tmp_path):
     e = np.loadtxt(tmp_path / "energy.dat", skiprows=1)
     assert len(e) == 3 and np.isfinite(e).all() and abs(e.mean() - 15.15) < 5
     assert os.path.exists(tmp_path / "configurations" / "walkers-Rank1.json")
+
+
+def test_host_driver_forward_walking_on_emulated_kernels(emu_lib):
+    env = _env(emu_lib)
+    env["QMC4_DMC_BIN"] = os.path.join(EMU_DIR, "dmc_b200_emu")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_host_driver.py"), "-q", "-m", "gpu",
+                        "-k", "forward_walking", "-p", "no:cacheprovider"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

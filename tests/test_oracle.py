@@ -189,3 +189,47 @@ def test_update_step_consistency(port):
     assert rej.any()
     np.testing.assert_array_equal(big["R"][rej], R[rej])
     np.testing.assert_array_equal(big["E"][rej], e0["E"][rej])
+
+
+# ---- forward walking (correlationEstimator.cpp) ---------------------------------------------------------
+FWD = np.load(os.path.join(GOLD, "forward_walking.npz")) if os.path.exists(os.path.join(GOLD, "forward_walking.npz")) else None
+
+
+def _fw_genealogy(name):
+    n = FWD[name + "/n"]
+    R, anc = FWD[name + "/R"], FWD[name + "/anc"]
+    edges = np.concatenate([[0], np.cumsum(n)])
+    pops = [R[edges[i]:edges[i + 1]] for i in range(len(n))]
+    ancs = [anc[edges[i]:edges[i + 1]] for i in range(len(n))]
+    return pops, ancs
+
+
+@pytest.mark.parametrize("name", sorted(cases.forward_walking_cases()))
+def test_forward_walking_matches_golden(port, name):
+    """storer ring + forward-walking estimator over a genealogy: the C restatement against what the
+    reference's own realHistogramStorer / realHistogramForwardWalkingEstimator produced"""
+    cfg = cases.forward_walking_cases()[name]
+    iM, meas = cases.fw_measurement(cfg)
+    pops, ancs = _fw_genealogy(name)
+    for steps in meas["forwardWalkingSteps"]:
+        sums, w = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, meas["bins"])
+        assert w == float(FWD["%s/fw%d/weight" % (name, steps)]) and w > 0
+        np.testing.assert_allclose(sums, FWD["%s/fw%d/sums" % (name, steps)], rtol=1e-13, atol=0)
+
+
+def test_forward_walking_matches_reference_itself(port, ref):
+    cfg = cases.forward_walking_cases()["pbc_pair"]
+    iM, meas = cases.fw_measurement(cfg)
+    pops, ancs = cases.synthetic_genealogy(cfg, 7, 5, 99)
+    for k, steps in enumerate(meas["forwardWalkingSteps"]):
+        a, wa = ref.forward_walking(cfg, pops, ancs, k, meas["bins"])
+        b, wb = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, meas["bins"])
+        assert wa == wb
+        np.testing.assert_allclose(b, a, rtol=1e-13, atol=0)
+
+
+def test_forward_walking_needs_steps_below_record_steps(port):
+    cfg = cases.forward_walking_cases()["pbc_pair"]
+    pops, ancs = cases.synthetic_genealogy(cfg, 3, 4, 1)
+    with pytest.raises(Exception):
+        port.forward_walking(cfg, pops, ancs, 0, 4, 4, 16)
