@@ -41,7 +41,10 @@ enum qmc_jastrow_kind {
   QMC_J_BSPLINE = 5,         /* "bSpline"         {stepSize,valueRight,derivativeRight,c_0..c_{n-1}} jastrowSpline.cpp:80-110 */
   QMC_J_POSCHTELLER = 6,     /* "poschTeller"     {R0,C,alpha,Rm,cut_off}        jastrowPoschTeller.h:19-57    */
   QMC_J_HARDSPHERE = 7,      /* "hardSphere"      {a,k,cut_off}                  jastrowHardSphereGauss.h:39-60*/
-  QMC_J_SQUAREWELL_BOUND = 8 /* "squareWellBoundState" {V0,R0,Rm,cut_off,aInverse,eb,alpha} jastrowSquareWell.h:80-150 */
+  QMC_J_SQUAREWELL_BOUND = 8,/* "squareWellBoundState" {V0,R0,Rm,cut_off,aInverse,eb,alpha} jastrowSquareWell.h:80-150 */
+  QMC_J_DELTA_PHONONS = 9,   /* "delta_phonons"   {k,delta,beta,z,cut_off}       jastrow_delta.h:4-54 (g is parsed, unused: process() is never called) */
+  QMC_J_DELTA_IN_TRAP = 10,  /* "delta_in_trap"   {a}                            jastrow_delta.h:56-72         */
+  QMC_J_DELTA_BOUND_STATE_PHONONS = 11 /* "delta_bound_state_phonons" {xI,k,A,beta,cut_off} jastrow_delta.h:74-98 */
 };
 
 /* ---- wavefunction terms (dmc/wavefunction/) ------------------------------------------------- */

@@ -89,6 +89,14 @@ static int radial_init(radial *J, int kind, const double *p, int np)
         J->a[6] = 2 * C * exp(-alpha * (lBox / 2.));
         return 0;
       }
+    case ORC_J_DELTA_PHONONS: /* jastrow_delta.cpp:5-39; p = {k,delta,beta,z,cut_off} */
+      for (int i = 0; i < 5; i++) J->a[i] = p[i];
+      J->a[5] = M_PI / (2 * p[4]);
+      return 0;
+    case ORC_J_DELTA_IN_TRAP: J->a[0] = p[0]; return 0;      /* jastrow_delta.cpp:71-74 */
+    case ORC_J_DELTA_BOUND_STATE_PHONONS: /* jastrow_delta.cpp:76-86; p = {xI,k,A,beta,cut_off} */
+      J->a[0] = p[0]; J->a[1] = p[1]; J->a[2] = log(p[2]); J->a[3] = p[3]; J->a[4] = M_PI / (p[4] * 2);
+      return 0;
     case ORC_J_BSPLINE: /* jastrowSpline.cpp:20-78; p = {stepSize,valueRight,derivativeRight,c...} */
       J->a[0] = 1. / p[0];
       J->a[1] = (np - 3 - 3) * p[0];
@@ -234,6 +242,28 @@ static void radial_eval(const radial *J, double x, double *d0, double *d1, doubl
             *d1 = 0;
             *d2 = 0;
           }
+        return;
+      }
+    case ORC_J_DELTA_PHONONS: /* jastrow_delta.h:14-17 (d0 = log(d0Exp), :50-53) */
+      {
+        double k = a[0], delta = a[1], beta = a[2], z = a[3], cut = a[4], k2 = a[5];
+        double e = (x < z) ? sin(k * x + delta) : x > cut ? sin(k * cut + delta) : pow(sin(k2 * x), beta);
+        *d0 = log(e);
+        *d1 = (x < z) ? k / tan(k * x + delta) : x > cut ? 0 : k2 * beta / tan(k2 * x);
+        *d2 = (x < z) ? -k * k / pow(sin(k * x + delta), 2) : x > cut ? 0 : -k2 * k2 * beta / pow(sin(k2 * x), 2);
+        return;
+      }
+    case ORC_J_DELTA_IN_TRAP: /* jastrow_delta.h:64-66 */
+      *d0 = log(x + a[0]);
+      *d1 = 1. / (x + a[0]);
+      *d2 = -(1. / pow(x + a[0], 2));
+      return;
+    case ORC_J_DELTA_BOUND_STATE_PHONONS: /* jastrow_delta.h:81-83 */
+      {
+        double xI = a[0], k = a[1], logA = a[2], beta = a[3], k2 = a[4];
+        *d0 = (x < xI) ? -k * x : logA + log(pow(sin(k2 * x), beta));
+        *d1 = (x < xI) ? -k : beta * k2 / tan(k2 * x);
+        *d2 = (x < xI) ? 0 : -k2 * beta * k2 / pow(sin(k2 * x), 2);
         return;
       }
     case ORC_J_BSPLINE: /* jastrowSpline.cpp:80-110 */

@@ -22,7 +22,8 @@ extern "C" {
 #endif
 
 enum { ORC_J_GAUSSIAN = 1, ORC_J_GAUSSGAUSS, ORC_J_SQUAREWELL, ORC_J_HARDSPHEREGAUSS, ORC_J_BSPLINE,
-       ORC_J_POSCHTELLER, ORC_J_HARDSPHERE, ORC_J_SQUAREWELL_BOUND };
+       ORC_J_POSCHTELLER, ORC_J_HARDSPHERE, ORC_J_SQUAREWELL_BOUND,
+       ORC_J_DELTA_PHONONS, ORC_J_DELTA_IN_TRAP, ORC_J_DELTA_BOUND_STATE_PHONONS };
 enum { ORC_WF_JASTROW1B = 1, ORC_WF_JASTROW2B_UNDIS, ORC_WF_JASTROW2B_DIS, ORC_WF_JASTROW3B_UNDIS };
 enum { ORC_POT_HARMONIC1B = 1, ORC_POT_SQUAREWELL2B, ORC_POT_DIPOLAR2B, ORC_POT_POSCHTELLER2B,
        ORC_POT_TWOBODY_SQUAREWELL, ORC_POT_TWOBODY_BARRIER, ORC_POT_THREEBODY_UNDIS_SQUAREWELL,

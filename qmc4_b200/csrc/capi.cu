@@ -247,6 +247,18 @@ int derive_radial(qmc_ctx *c, int kind, const double *p, int np, RadialFn &J)
         J.p[8] = B; J.p[9] = C; J.p[10] = log(B + C * 2 * exp(-alpha * half));
         return 0;
       }
+    case QMC_J_DELTA_PHONONS: /* jastrow_delta.cpp:5-39: parameters as given, k2 = pi/(2 cut_off) */
+      if (!need(5)) return fail(c, "delta_phonons: {k,delta,beta,z,cut_off}");
+      J.p[0] = p[0]; J.p[1] = p[1]; J.p[2] = p[2]; J.p[3] = p[3]; J.p[4] = p[4]; J.p[5] = M_PI / (2 * p[4]);
+      return 0;
+    case QMC_J_DELTA_IN_TRAP: /* jastrow_delta.cpp:71-74 */
+      if (!need(1)) return fail(c, "delta_in_trap: {a}");
+      J.p[0] = p[0];
+      return 0;
+    case QMC_J_DELTA_BOUND_STATE_PHONONS: /* jastrow_delta.cpp:76-86: lBox = 2 cut_off, k2 = pi/lBox */
+      if (!need(5)) return fail(c, "delta_bound_state_phonons: {xI,k,A,beta,cut_off}");
+      J.p[0] = p[0]; J.p[1] = p[1]; J.p[2] = log(p[2]); J.p[3] = p[3]; J.p[4] = M_PI / (p[4] * 2);
+      return 0;
     case QMC_J_HARDSPHEREGAUSS: /* jastrowHardSphereGauss.cpp:4-16 */
       {
         if (!need(3)) return fail(c, "hardSphereGauss: {a,Rm,D}");

@@ -14,6 +14,9 @@
 //   POSCHTELLER     p0=Rm p1=halfLBox p2=K0 p3=alpha p4=lBox p5=C p6=longDistanceConstant
 //   HARDSPHERE      p0=a p1=cutOff p2=A p3=k
 //   SQUAREWELL_BOUND p0=R0 p1=Rm p2=halfLBox p3=K0 p4=logA p5=expCoeff p6=alpha p7=lBox p8=B p9=C p10=longDistanceConstant
+//   DELTA_PHONONS   p0=k p1=delta p2=beta p3=z p4=cut_off p5=k2(=pi/(2 cut_off))
+//   DELTA_IN_TRAP   p0=a
+//   DELTA_BOUND_STATE_PHONONS p0=xI p1=k p2=logA p3=beta p4=k2(=pi/(2 cut_off))
 #pragma once
 #include "plan.h"
 #include "device_math.cuh"
@@ -163,6 +166,54 @@ static __device__ QMC_NOINLINE void eval_radial(const RadialFn &J, const double 
             d0 = p[6];
             d1 = 0;
             d2 = 0;
+          }
+        return;
+      }
+    case J_DELTA_PHONONS: /* jastrow_delta.h:14-17,50-53 */
+      {
+        const double k = p[0], delta = p[1], beta = p[2], z = p[3], cut = p[4], k2 = p[5];
+        if (r < z)
+          {
+            double s = sin(k * r + delta);
+            d0 = log(s);
+            d1 = k / tan(k * r + delta);
+            d2 = -k * k / (s * s);
+          }
+        else if (r > cut)
+          {
+            d0 = log(sin(k * cut + delta));      /* sic: the inner branch evaluated at the cut-off */
+            d1 = 0;
+            d2 = 0;
+          }
+        else
+          {
+            double s = sin(k2 * r);
+            d0 = log(pow(s, beta));
+            d1 = k2 * beta / tan(k2 * r);
+            d2 = -k2 * k2 * beta / (s * s);
+          }
+        return;
+      }
+    case J_DELTA_IN_TRAP: /* jastrow_delta.h:64-66 */
+      d0 = log(r + p[0]);
+      d1 = 1. / (r + p[0]);
+      d2 = -(1. / ((r + p[0]) * (r + p[0])));
+      return;
+    case J_DELTA_BOUND_STATE_PHONONS: /* jastrow_delta.h:81-83 */
+      {
+        const double xI = p[0], k = p[1], logA = p[2], beta = p[3], k2 = p[4];
+        if (r < xI)
+          {
+            d0 = -k * r;
+            d1 = -k;
+            d2 = 0;
+          }
+        else
+          {
+            double s = sin(k2 * r);
+            d0 = logA + log(pow(s, beta));
+            d1 = beta * k2 / tan(k2 * r);
+            d2 = -k2 * beta * k2 / (s * s);
           }
         return;
       }

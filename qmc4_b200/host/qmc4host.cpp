@@ -167,6 +167,9 @@ void registerDefaults(factory &f)
   f.registerJastrow<jastrowHardSphereGauss>();
   f.registerJastrow<jastrowHardSphere>();
   f.registerJastrow<jastrowSpline>();
+  f.registerJastrow<jastrow_delta_phonons>();                /* main.cpp:213-215 */
+  f.registerJastrow<jastrow_delta_in_trap>();
+  f.registerJastrow<jastrow_delta_bound_state_phonons>();
   f.registerObservable<pairCorrelation>();
   f.registerObservable<trimerCorrelationUnDis>();
   f.registerObservable<structureFactor>();

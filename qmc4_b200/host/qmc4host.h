@@ -66,7 +66,35 @@ QMC_JASTROW(jastrowSquareWellBoundState, "squareWellBoundState", QMC_J_SQUAREWEL
 QMC_JASTROW(jastrowPoschTeller, "poschTeller", QMC_J_POSCHTELLER, "R0", "C", "alpha", "Rm", "cut_off");
 QMC_JASTROW(jastrowHardSphereGauss, "hardSphereGauss", QMC_J_HARDSPHEREGAUSS, "a", "Rm", "D");
 QMC_JASTROW(jastrowHardSphere, "hardSphere", QMC_J_HARDSPHERE, "a", "k", "cut_off");
+QMC_JASTROW(jastrow_delta_in_trap, "delta_in_trap", QMC_J_DELTA_IN_TRAP, "a");                        // jastrow_delta.cpp:71-74
 #undef QMC_JASTROW
+struct jastrow_delta_phonons : jastrowBase {                                                          // jastrow_delta.cpp:5-39
+  static std::string name() { return "delta_phonons"; }
+  explicit jastrow_delta_phonons(const json_t &j)
+  {
+    kind = QMC_J_DELTA_PHONONS;
+    for (const char *k : {"k", "delta", "beta", "z", "cut_off"}) params.push_back(j[k].get<real_t>());
+    try
+      {
+        (void)j["g"].get<real_t>();        /* parsed for process(), which the reference never calls */
+      }
+    catch (invalidType &)
+      {
+        if (j["g"].get<std::string>() != "inf") throw invalidInput("g is not a number and is not infinite");
+      }
+  }
+};
+struct jastrow_delta_bound_state_phonons : jastrowBase {                                              // jastrow_delta.cpp:76-86
+  static std::string name() { return "delta_bound_state_phonons"; }
+  explicit jastrow_delta_bound_state_phonons(const json_t &j)
+  {
+    kind = QMC_J_DELTA_BOUND_STATE_PHONONS;
+    const real_t xI = j["xI"].get<real_t>(), g = j["g"].get<real_t>(), cut = j["cut_off"].get<real_t>(), k = j["k"].get<real_t>(),
+                 A = j["A"].get<real_t>(), beta = j["beta"].get<real_t>();
+    (void)g;
+    params = {xI, k, A, beta, cut};
+  }
+};
 struct jastrowSpline : jastrowBase {                                                                  // jastrowSpline.cpp:20-22
   static std::string name() { return "bSpline"; }
   explicit jastrowSpline(const json_t &j)

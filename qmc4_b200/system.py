@@ -45,6 +45,22 @@ def _get(j, key):
     return j[key]
 
 
+def _delta_phonons(j):
+    """jastrow_delta.cpp:5-39: k, delta, beta, z, cut_off are read in this order, then g, which must be a number or the
+    string "inf" (it only matters to process(), which the reference never calls)"""
+    p = [_get(j, k) for k in ("k", "delta", "beta", "z", "cut_off")]
+    g = _get(j, "g")
+    if isinstance(g, str) and g != "inf":
+        raise invalidInput("g is not a number and is not infinite")
+    return p
+
+
+def _delta_bound_state(j):
+    """jastrow_delta.cpp:76-86 reads xI, g, cut_off, k, A, beta (all required; g is stored, never used)"""
+    v = {k: _get(j, k) for k in ("xI", "g", "cut_off", "k", "A", "beta")}
+    return [v["xI"], v["k"], v["A"], v["beta"], v["cut_off"]]
+
+
 # radial functor name -> (C kind, parameter extractor) ; mirrors the JSON constructors
 _JASTROWS = {
     "gaussian": (capi.J_GAUSSIAN, lambda j: [_get(j, "alpha")]),
@@ -55,6 +71,9 @@ _JASTROWS = {
     "poschTeller": (capi.J_POSCHTELLER, lambda j: [_get(j, k) for k in ("R0", "C", "alpha", "Rm", "cut_off")]),
     "hardSphere": (capi.J_HARDSPHERE, lambda j: [_get(j, k) for k in ("a", "k", "cut_off")]),
     "squareWellBoundState": (capi.J_SQUAREWELL_BOUND, lambda j: [_get(j, k) for k in ("V0", "R0", "Rm", "cut_off", "aInverse", "eb", "alpha")]),
+    "delta_phonons": (capi.J_DELTA_PHONONS, lambda j: _delta_phonons(j)),
+    "delta_in_trap": (capi.J_DELTA_IN_TRAP, lambda j: [_get(j, "a")]),
+    "delta_bound_state_phonons": (capi.J_DELTA_BOUND_STATE_PHONONS, lambda j: _delta_bound_state(j)),
 }
 _WAVES = {"jastrow1b": capi.WF_JASTROW1B, "jastrow2bUnDis": capi.WF_JASTROW2B_UNDIS,
           "jastrow2bDis": capi.WF_JASTROW2B_DIS, "jastrow3bUnDis": capi.WF_JASTROW3B_UNDIS}

@@ -63,6 +63,10 @@ JASTROWS = {
     "squareWellBoundState": {"kind": "squareWellBoundState", "V0": 6.0, "R0": 1.0, "Rm": 1.5, "cut_off": 2.5, "aInverse": 0.5, "eb": 0.25, "alpha": 0.7},
     "bSpline": {"kind": "bSpline", "stepSize": 0.025, "valueRight": -1.0, "derivativeRight": -0.5,
                 "coefficients": [-(0.025 * (i - 1)) ** 2 * 0.16 for i in range(0, 103)]},
+    "delta_phonons": {"kind": "delta_phonons", "k": 0.9, "delta": 0.35, "beta": 1.3, "z": 0.8, "cut_off": 2.2, "g": 2.0},
+    "delta_phonons_ginf": {"kind": "delta_phonons", "k": 0.7, "delta": 0.5, "beta": 0.9, "z": 1.1, "cut_off": 2.4, "g": "inf"},
+    "delta_in_trap": {"kind": "delta_in_trap", "a": 0.3},
+    "delta_bound_state_phonons": {"kind": "delta_bound_state_phonons", "xI": 0.9, "g": -1.0, "cut_off": 2.3, "k": 0.6, "A": 1.7, "beta": 1.2}
 }
 
 
