@@ -139,14 +139,23 @@ def cpu_reference_arm(cfg, seconds_budget, max_procs=None):
     one single-rank process per core with seed+core — its own decomposition (main.cpp:383,391) —
     on a bounded sample of the workload.  Falls back to the C restatement when the binary is absent."""
     from oracle import oracle as orc
-    cores = os.cpu_count() or 1
+    cpu_ids = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    cores = len(cpu_ids)
     if max_procs:
         cores = min(cores, max_procs)
     N = sum(cfg["N"])
     pairs, trip, _, _ = work_per_move(cfg)
     if os.path.exists(orc.REF_BIN):
         est_us = 0.12 * (pairs + 6 * trip) + 25.0 * N / 10 + 5           # planning estimate per walker-move
-        w_cpu = 64
+        # the reference caches a 32*P-byte distance table per walker in two containers (SURVEY §8 a1: 4.2 MB per
+        # walker at N=512): bound one process to ~256 MB and all processes to a quarter of the free host memory
+        per_walker = 2 * (32.0 * max(pairs, 1) + 200.0 * N) + 4096
+        w_cpu = int(max(8, min(64, 256e6 // per_walker)))
+        try:
+            avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+            cores = int(max(1, min(cores, 0.25 * avail // (per_walker * w_cpu * 1.5 + 64e6))))
+        except (OSError, IndexError, ValueError):
+            pass
         steps = int(max(4, min(400, seconds_budget * 1e6 / (est_us * w_cpu))))
         spb = max(1, steps // 4)
         c = dict(cfg)
@@ -162,7 +171,7 @@ def cpu_reference_arm(cfg, seconds_budget, max_procs=None):
             json.dump(ck, open(os.path.join(d, "input.json"), "w"))
             cmd = [orc.REF_BIN, "input.json"]
             if hasattr(os, "sched_setaffinity"):
-                cmd = ["taskset", "-c", str(k)] + cmd
+                cmd = ["taskset", "-c", str(cpu_ids[k])] + cmd
             procs.append(subprocess.Popen(cmd, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
         moves, rate = 0.0, 0.0
         for p in procs:
@@ -209,7 +218,11 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=1500, help="seconds after which a hung run dumps every thread's stack to stderr and exits")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     steps, warmup = args.steps, max(args.warmup, 3)
     wpg = args.walkers or DEFAULT_WALKERS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -352,7 +365,7 @@ def main():
             "kernel": {"warps_per_walker": s.info("warps_per_walker"), "grid": s.info("grid"), "smem_bytes": s.info("smem_bytes"),
                        "regs": s.info("regs_propagate"), "variant": s.info("kernel_variant")}}
     s.close()
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # rank 0 at N=1 only (the N>1 runs compare against the same number)
         line["cpu_baseline"] = cpu_reference_arm(cfg, seconds_budget=12.0)
     print(json.dumps(line))
 

@@ -1019,6 +1019,13 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
     }
   CK(cudaMalloc(&c->parent, capacity * 4));
   CK(cudaMalloc(&c->n_desc, capacity * 4));
+  if (c->nranks > 1)
+    { /* migration slabs sized once for a quarter of the capacity: no cudaMalloc/cudaFree (device-wide
+         synchronisation) between the ranks' NCCL calls of qmc_rebalance in the common case */
+      c->slab_bytes = (size_t)(capacity / 4 + 1) * (2 * dofs + 2) * 8;
+      CK(cudaMalloc(&c->slab_send, c->slab_bytes));
+      CK(cudaMalloc(&c->slab_recv, c->slab_bytes));
+    }
   if (c->pipeline == 2) CK(cudaMalloc(&c->e_old, capacity * 8));
   c->cfg.grid = grid_for(c, capacity);
   c->n_partials = c->cfg.grid * c->cfg.groups_per_cta;

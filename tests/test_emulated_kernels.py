@@ -53,10 +53,13 @@ def test_shipped_library_has_no_emulation_marker():
     assert not hasattr(ctypes.CDLL(lib), "qmc_emulated")
 
 
-def test_parity_suite_on_emulated_kernels(emu_lib):
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
+@pytest.mark.parametrize("suite", ["test_gpu_parity.py", "test_zz_gpu_new_paths.py"])
+def test_parity_suite_on_emulated_kernels(emu_lib, suite):
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", suite), "-q", "-x",
                         "-m", "gpu", "-k", FAST, "-p", "no:cacheprovider"],
-                       env=_env(emu_lib), cwd=ROOT, capture_output=True, text=True, timeout=1500)
+                       env=dict(_env(emu_lib), QMC4_DMC_BIN=os.path.join(EMU_DIR, "dmc_b200_emu"), QMC4_EMU_DEVICES="1",
+                                QMC4_NCCL_LIB=os.path.join(EMU_DIR, "libnccl_emu.so")),
+                       cwd=ROOT, capture_output=True, text=True, timeout=1500)
     tail = "\n".join(r.stdout.splitlines()[-25:])
     assert r.returncode == 0, tail + r.stderr[-2000:]
     assert " passed" in tail and "failed" not in tail, tail
@@ -134,11 +137,3 @@ def test_host_driver_two_gpu_threads_on_emulated_kernels(emu_lib, tmp_path):
     e = np.loadtxt(tmp_path / "energy.dat", skiprows=1)
     assert len(e) == 3 and np.isfinite(e).all() and abs(e.mean() - 15.15) < 5
     assert os.path.exists(tmp_path / "configurations" / "walkers-Rank1.json")
-
-
-def test_host_driver_forward_walking_on_emulated_kernels(emu_lib):
-    env = _env(emu_lib)
-    env["QMC4_DMC_BIN"] = os.path.join(EMU_DIR, "dmc_b200_emu")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_host_driver.py"), "-q", "-m", "gpu",
-                        "-k", "forward_walking", "-p", "no:cacheprovider"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

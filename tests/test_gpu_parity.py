@@ -328,78 +328,3 @@ def test_dmc_statistical_parity_with_reference_run(name):
         z = np.abs(g.mean(0) - g_ref.mean(0)) / np.maximum(sg, 1e-12)
         # bins are correlated; require the bulk within 2 sigma and none beyond 4
         assert (z < 2).mean() > 0.8 and z.max() < 4, z
-
-
-# ---- forward walking (kernels_fw.cu) ---------------------------------------------------
-def _traced_genealogy(s, cfg, events, sample_every, rng):
-    """run events*sample_every traced DMC steps; returns the post-branching populations at the sampling
-    events and, for each, the index of every walker's ancestor in the previous event's population"""
-    W = cfg["walkers"]
-    L = np.asarray(cfg["lBox"], dtype=float)
-    cols = [(rng.uniform(-0.5, 0.5, size=(W, 3, N)) * L[None, :, None]).reshape(W, -1) for N in cfg["N"]]
-    s.upload(np.concatenate(cols, axis=1))
-    pops, ancs, comp = [], [], None
-    for t in range(events * sample_every):
-        sample = (t + 1) % sample_every == 0
-        tr = s.step_traced(accumulate=sample)
-        step_anc = np.repeat(np.arange(tr["n_before"]), tr["n_desc"][:tr["n_before"]])     # branching.cpp:34-61 as a map
-        assert len(step_anc) == tr["n_after"]
-        comp = step_anc if comp is None else comp[step_anc]
-        if sample:
-            R, _ = s.download(with_energy=True)
-            pops.append(R)
-            ancs.append(comp.astype(np.int32) if len(pops) > 1 else np.arange(len(R), dtype=np.int32))
-            comp = None
-    return pops, ancs
-
-
-@pytest.mark.parametrize("sample_every", [1, 3])
-@pytest.mark.parametrize("name", sorted(cases.forward_walking_cases()))
-def test_forward_walking_vs_oracle_on_the_traced_genealogy(port, name, sample_every):
-    """the device never copies a record: it must still reproduce the reference's per-walker rings that are
-    deep-copied at every branching, for the genealogy the run actually produced"""
-    cfg = cases.forward_walking_cases()[name]
-    iM, meas = cases.fw_measurement(cfg)
-    s = System.from_input(cfg)
-    assert s.info("fw_depth") == max(meas["forwardWalkingSteps"]) + 1
-    pops, ancs = _traced_genealogy(s, cfg, 9, sample_every, np.random.default_rng(3))
-    assert len({len(p) for p in pops}) > 1, "no branching happened: the test would not exercise the genealogy"
-    labels = [e["label"] for e in s.estimators]
-    for steps in meas["forwardWalkingSteps"]:
-        e = s.estimators[labels.index("%s_fw%d" % (meas["label"], steps))]     # estimatorsFactory.cpp:58
-        got, w = s.estimator(e["index"])
-        exp, we = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, meas["bins"])
-        assert w == we and w > 0
-        assert rel(got, exp) < RTOL, steps
-    assert meas["label"] not in labels                 # the plain estimator is replaced, not added (estimatorsFactory.cpp:47)
-    s.clear_estimators()
-    got, w = s.estimator(s.estimators[0]["index"])
-    assert w == 0 and not got.any()
-    s.close()
-
-
-def test_forward_walking_ring_restarts_with_a_new_population(port):
-    cfg = cases.forward_walking_cases()["pbc_pair"]
-    iM, meas = cases.fw_measurement(cfg)
-    s = System.from_input(cfg)
-    rng = np.random.default_rng(8)
-    _traced_genealogy(s, cfg, 5, 1, rng)
-    s.clear_estimators()
-    pops, ancs = _traced_genealogy(s, cfg, 6, 1, rng)          # upload: storer::reserve, rings filling again
-    assert s.info("fw_events") == 6
-    e = s.estimators[0]
-    got, w = s.estimator(e["index"])
-    exp, we = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], e["forwardWalkingSteps"], meas["bins"])
-    assert w == we and rel(got, exp) < RTOL
-    s.close()
-
-
-def test_forward_walking_errors():
-    cfg = cases.structure_factor()
-    cfg["measurements"][0].update(recordSteps=4, forwardWalkingSteps=[1])
-    with pytest.raises(Exception, match="Forward walking estimator for vector"):      # estimatorsFactory.cpp:66-69
-        System.from_input(cfg)
-    cfg = cases.forward_walking_cases()["pbc_pair"]
-    cfg["measurements"][0]["forwardWalkingSteps"] = [4]                                # assert, correlationEstimator.cpp:137
-    with pytest.raises(Exception, match="recordSteps"):
-        System.from_input(cfg)

@@ -117,34 +117,3 @@ def test_multi_gpu_threads(tmp_path):
     e = np.loadtxt(tmp_path / "energy.dat", skiprows=1)
     assert len(e) == 20 and abs(e[8:].mean() - 15.15) < 0.5
     assert os.path.exists(tmp_path / "configurations" / "walkers-Rank1.json")
-
-
-@pytest.mark.gpu
-def test_forward_walking_measurement_files(tmp_path):
-    """"recordSteps" + "forwardWalkingSteps": [..] on a measurement: one <label>_fw<steps>.dat per entry instead of
-    <label>.dat (estimatorsFactory.cpp:47-74), rows at the bin CENTRES (accumulators.h:146-156), nothing but the
-    blank separator while the walkers' rings are filling (correlationEstimator.cpp:171-178)"""
-    cfg = cases.forward_walking_cases()["pbc_pair"]
-    cfg = dict(cfg, stepsPerBlock=3, nBlocks=3, correlationSteps=1)
-    p = run(cfg, str(tmp_path))
-    assert p.returncode == 0, p.stderr
-    m = cfg["measurements"][0]
-    assert not os.path.exists(tmp_path / (m["label"] + ".dat"))
-    dx = (m["maxx"] - m["minx"]) / m["bins"]
-    for steps in m["forwardWalkingSteps"]:
-        txt = open(tmp_path / ("%s_fw%d.dat" % (m["label"], steps))).read()
-        lines = txt.split("\n")
-        assert lines[0] == "x %s_fw%d" % (m["label"], steps)
-        blocks = [b for b in txt[len(lines[0]) + 1:].split("\n\n")]
-        # block 0: 3 sampling events < recordSteps = 4 -> no rows; blocks 1 and 2: bins rows each
-        rows = [[r for r in b.split("\n") if r.strip()] for b in blocks]
-        rows = [r for r in rows if r]
-        assert len(rows) == 2 and all(len(r) == m["bins"] for r in rows), [len(r) for r in rows]
-        first = np.array([[float(v) for v in r.split()] for r in rows[0]])
-        np.testing.assert_allclose(first[:, 0], m["minx"] + (np.arange(m["bins"]) + 0.5) * dx, rtol=1e-5)
-        assert np.isfinite(first[:, 1]).all() and first[:, 1].sum() > 0
-    # the structure factor has no forward-walking estimator in the reference either
-    bad = cases.structure_factor()
-    bad["measurements"][0].update(recordSteps=4, forwardWalkingSteps=[1])
-    p = run(bad, str(tmp_path))
-    assert p.returncode != 0 and "Forward walking estimator for vector" in p.stderr

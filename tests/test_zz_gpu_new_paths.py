@@ -1,0 +1,127 @@
+"""GPU parity tests (-m gpu) of the paths that were written while no B200 time was left in round 1:
+forward walking and the §8(f)2-4 widening.  Their logic is parity-green on the thread
+emulation of the CUDA sources (tests/test_emulated_kernels.py runs this file against tests/emu), but they
+have not executed on hardware yet — the file sorts last so that, under `pytest -x`, a hardware-only failure
+here cannot hide the suite that was validated on the B200 (test_gpu_parity.py, test_host_driver.py).
+Tolerance for floating point: 1e-10 relative (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import test_host_driver as hd
+from qmc4_b200.system import System
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+# ---- forward walking (kernels_fw.cu) ---------------------------------------------------
+def _traced_genealogy(s, cfg, events, sample_every, rng):
+    """run events*sample_every traced DMC steps; returns the post-branching populations at the sampling
+    events and, for each, the index of every walker's ancestor in the previous event's population"""
+    W = cfg["walkers"]
+    L = np.asarray(cfg["lBox"], dtype=float)
+    cols = [(rng.uniform(-0.5, 0.5, size=(W, 3, N)) * L[None, :, None]).reshape(W, -1) for N in cfg["N"]]
+    s.upload(np.concatenate(cols, axis=1))
+    pops, ancs, comp = [], [], None
+    for t in range(events * sample_every):
+        sample = (t + 1) % sample_every == 0
+        tr = s.step_traced(accumulate=sample)
+        step_anc = np.repeat(np.arange(tr["n_before"]), tr["n_desc"][:tr["n_before"]])     # branching.cpp:34-61 as a map
+        assert len(step_anc) == tr["n_after"]
+        comp = step_anc if comp is None else comp[step_anc]
+        if sample:
+            R, _ = s.download(with_energy=True)
+            pops.append(R)
+            ancs.append(comp.astype(np.int32) if len(pops) > 1 else np.arange(len(R), dtype=np.int32))
+            comp = None
+    return pops, ancs
+
+
+@pytest.mark.parametrize("sample_every", [1, 3])
+@pytest.mark.parametrize("name", sorted(cases.forward_walking_cases()))
+def test_forward_walking_vs_oracle_on_the_traced_genealogy(port, name, sample_every):
+    """the device never copies a record: it must still reproduce the reference's per-walker rings that are
+    deep-copied at every branching, for the genealogy the run actually produced"""
+    cfg = cases.forward_walking_cases()[name]
+    iM, meas = cases.fw_measurement(cfg)
+    s = System.from_input(cfg)
+    assert s.info("fw_depth") == max(meas["forwardWalkingSteps"]) + 1
+    pops, ancs = _traced_genealogy(s, cfg, 9, sample_every, np.random.default_rng(3))
+    assert len({len(p) for p in pops}) > 1, "no branching happened: the test would not exercise the genealogy"
+    labels = [e["label"] for e in s.estimators]
+    for steps in meas["forwardWalkingSteps"]:
+        e = s.estimators[labels.index("%s_fw%d" % (meas["label"], steps))]     # estimatorsFactory.cpp:58
+        got, w = s.estimator(e["index"])
+        exp, we = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, meas["bins"])
+        assert w == we and w > 0
+        assert rel(got, exp) < RTOL, steps
+    assert meas["label"] not in labels                 # the plain estimator is replaced, not added (estimatorsFactory.cpp:47)
+    s.clear_estimators()
+    got, w = s.estimator(s.estimators[0]["index"])
+    assert w == 0 and not got.any()
+    s.close()
+
+
+def test_forward_walking_ring_restarts_with_a_new_population(port):
+    cfg = cases.forward_walking_cases()["pbc_pair"]
+    iM, meas = cases.fw_measurement(cfg)
+    s = System.from_input(cfg)
+    rng = np.random.default_rng(8)
+    _traced_genealogy(s, cfg, 5, 1, rng)
+    s.clear_estimators()
+    pops, ancs = _traced_genealogy(s, cfg, 6, 1, rng)          # upload: storer::reserve, rings filling again
+    assert s.info("fw_events") == 6
+    e = s.estimators[0]
+    got, w = s.estimator(e["index"])
+    exp, we = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], e["forwardWalkingSteps"], meas["bins"])
+    assert w == we and rel(got, exp) < RTOL
+    s.close()
+
+
+def test_forward_walking_errors():
+    cfg = cases.structure_factor()
+    cfg["measurements"][0].update(recordSteps=4, forwardWalkingSteps=[1])
+    with pytest.raises(Exception, match="Forward walking estimator for vector"):      # estimatorsFactory.cpp:66-69
+        System.from_input(cfg)
+    cfg = cases.forward_walking_cases()["pbc_pair"]
+    cfg["measurements"][0]["forwardWalkingSteps"] = [4]                                # assert, correlationEstimator.cpp:137
+    with pytest.raises(Exception, match="recordSteps"):
+        System.from_input(cfg)
+
+
+def test_forward_walking_measurement_files(tmp_path):
+    """"recordSteps" + "forwardWalkingSteps": [..] on a measurement: one <label>_fw<steps>.dat per entry instead of
+    <label>.dat (estimatorsFactory.cpp:47-74), rows at the bin CENTRES (accumulators.h:146-156), nothing but the
+    blank separator while the walkers' rings are filling (correlationEstimator.cpp:171-178)"""
+    cfg = cases.forward_walking_cases()["pbc_pair"]
+    cfg = dict(cfg, stepsPerBlock=3, nBlocks=3, correlationSteps=1)
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    m = cfg["measurements"][0]
+    assert not os.path.exists(tmp_path / (m["label"] + ".dat"))
+    dx = (m["maxx"] - m["minx"]) / m["bins"]
+    for steps in m["forwardWalkingSteps"]:
+        txt = open(tmp_path / ("%s_fw%d.dat" % (m["label"], steps))).read()
+        lines = txt.split("\n")
+        assert lines[0] == "x %s_fw%d" % (m["label"], steps)
+        blocks = [b for b in txt[len(lines[0]) + 1:].split("\n\n")]
+        # block 0: 3 sampling events < recordSteps = 4 -> no rows; blocks 1 and 2: bins rows each
+        rows = [[r for r in b.split("\n") if r.strip()] for b in blocks]
+        rows = [r for r in rows if r]
+        assert len(rows) == 2 and all(len(r) == m["bins"] for r in rows), [len(r) for r in rows]
+        first = np.array([[float(v) for v in r.split()] for r in rows[0]])
+        np.testing.assert_allclose(first[:, 0], m["minx"] + (np.arange(m["bins"]) + 0.5) * dx, rtol=1e-5)
+        assert np.isfinite(first[:, 1]).all() and first[:, 1].sum() > 0
+    # the structure factor has no forward-walking estimator in the reference either
+    bad = cases.structure_factor()
+    bad["measurements"][0].update(recordSteps=4, forwardWalkingSteps=[1])
+    p = hd.run(bad, str(tmp_path))
+    assert p.returncode != 0 and "Forward walking estimator for vector" in p.stderr
