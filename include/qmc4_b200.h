@@ -52,7 +52,9 @@ enum qmc_wavefunction_kind {
   QMC_WF_JASTROW1B = 1,       /* "jastrow1b/<J>"      sets={A}      jastrowWavefunctionOneBody.h:53-85   */
   QMC_WF_JASTROW2B_UNDIS = 2, /* "jastrow2bUnDis/<J>" sets={A,A}    jastrowWavefunctionTwoBody.h:124-164 */
   QMC_WF_JASTROW2B_DIS = 3,   /* "jastrow2bDis/<J>"   sets={A,B}    jastrowWavefunctionTwoBody.h:33-76   */
-  QMC_WF_JASTROW3B_UNDIS = 4  /* "jastrow3bUnDis/<J>" sets={A}      jastrowWavefunctionThreeBody.h:91-137*/
+  QMC_WF_JASTROW3B_UNDIS = 4, /* "jastrow3bUnDis/<J>" sets={A}      jastrowWavefunctionThreeBody.h:91-137*/
+  QMC_WF_JASTROW3B_DIS = 5    /* "jastrow3bDis/<J>"   sets={A,B,C} (all different)  jastrowWavefunctionThreeBody.h:164-305;
+                                 hardSphereRadius -> hardSphereConstraintThreeBodyDis (jastrowWavefunctionThreeBody.cpp:39-80) */
 };
 
 /* ---- potentials (dmc/potential.cpp, potentialTwoBody.h, potentialThreeBody.h) ---------------- */
@@ -64,16 +66,26 @@ enum qmc_potential_kind {
   QMC_POT_TWOBODY_SQUAREWELL = 5,  /* "potentialTwoBody/squareWell"        sets={A,B} params={R0,V0}  potentialTwoBody.h:23-33, potentialFunctors.h:5-19  */
   QMC_POT_TWOBODY_BARRIER = 6,     /* "potentialTwoBody/potentialBarrier"  sets={A,B} params={R0,V0}  potentialFunctors.h:22-36 */
   QMC_POT_THREEBODY_UNDIS_SQUAREWELL = 7, /* "potentialThreeBodyUnDis/squareWell"       sets={A,A,A} params={R0,V0} potentialThreeBody.h:23-44 */
-  QMC_POT_THREEBODY_UNDIS_BARRIER = 8     /* "potentialThreeBodyUnDis/potentialBarrier" sets={A,A,A} params={R0,V0} */
+  QMC_POT_THREEBODY_UNDIS_BARRIER = 8,    /* "potentialThreeBodyUnDis/potentialBarrier" sets={A,A,A} params={R0,V0} */
+  QMC_POT_THREEBODY_DIS_SQUAREWELL = 9,   /* "potentialThreeBodyDis/squareWell"         sets={A,B,C} params={R0,V0} potentialThreeBody.h:60-125 */
+  QMC_POT_THREEBODY_DIS_BARRIER = 10      /* "potentialThreeBodyDis/potentialBarrier"   sets={A,B,C} params={R0,V0} */
 };
 
 /* ---- estimators accumulated every sampling step (dmc/estimatorsFactory.cpp:39-133) ----------- */
 enum qmc_estimator_kind {
   QMC_EST_PAIRCORRELATION = 1,       /* "pairCorrelation"        sets={A,B}  pairCorrelation.cpp:17-59   */
   QMC_EST_TRIMERCORRELATION_UNDIS = 2, /* "trimerCorrelationUnDis" sets={A}  trimerCorrelation.cpp:82-143 */
-  QMC_EST_STRUCTUREFACTOR = 3        /* "structureFactor" sets={A,B} extra={maxq,lBox,channel}; bins q-points
+  QMC_EST_STRUCTUREFACTOR = 3,       /* "structureFactor" sets={A,B} extra={maxq,lBox,channel}; bins q-points
                                         (structureFactor.cpp:8-90, applied to coordinate 0 — the reference
                                         compiles it for DIMENSIONS==1 only) */
+  QMC_EST_TRIMERCORRELATION = 4,     /* "trimerCorrelation"    sets={A,B,C}, N_C must be 1 (assert, trimerCorrelation.cpp:11);
+                                        normalisation 1/(dx 4 pi N_A N_B N_B) as in the reference (:69, sic) */
+  QMC_EST_TRIMERCORRELATION_DIS = 5, /* "trimerCorrelationDis" sets={A,B,C}  trimerCorrelation.cpp:163-227 */
+  /* scalar observables (realScalarEstimator, estimators.cpp:35-48,89-98): bins must be 1, minx/maxx unused;
+     qmc_get_estimator returns sums[0] = sum of the observable over the accumulated walkers and their number in
+     *weight (scalarAccumulator, accumulators.h:21-47: average = sum/n) */
+  QMC_EST_TRIMERHYPERRADIUS = 6,     /* "trimerhyperRadius"    sets={A,B,C}, N_C must be 1   hyperRadius.cpp:17-43 */
+  QMC_EST_CENTEROFMASSSQUARED = 7    /* "centerOfMassSquared"  sets={A}   centerOfMassSquared.cpp:8-18: (sum_i |r_i|)^2/N */
 };
 
 /* Results of one block, the numbers dmcDriver::out() prints and dumps (dmc/dmcDriver.cpp:197-230). */

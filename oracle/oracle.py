@@ -157,11 +157,14 @@ _J = {"gaussian": (1, ("alpha",)), "gaussiangaussian": (2, ("r0", "u0")),
       "squareWellBoundState": (8, ("V0", "R0", "Rm", "cut_off", "aInverse", "eb", "alpha")),
       "delta_phonons": (9, ("k", "delta", "beta", "z", "cut_off")), "delta_in_trap": (10, ("a",)),
       "delta_bound_state_phonons": (11, ("xI", "k", "A", "beta", "cut_off"))}
-_WF = {"jastrow1b": 1, "jastrow2bUnDis": 2, "jastrow2bDis": 3, "jastrow3bUnDis": 4}
+_WF = {"jastrow1b": 1, "jastrow2bUnDis": 2, "jastrow2bDis": 3, "jastrow3bUnDis": 4, "jastrow3bDis": 5}
 _POT = {"harmonic1b": 1, "squareWell2b": 2, "dipolar2b": 3, "poschTeller2b": 4, "potentialTwoBody/squareWell": 5,
         "potentialTwoBody/potentialBarrier": 6, "potentialThreeBodyUnDis/squareWell": 7,
-        "potentialThreeBodyUnDis/potentialBarrier": 8}
-_EST = {"pairCorrelation": 1, "trimerCorrelationUnDis": 2, "structureFactor": 3}
+        "potentialThreeBodyUnDis/potentialBarrier": 8, "potentialThreeBodyDis/squareWell": 9,
+        "potentialThreeBodyDis/potentialBarrier": 10}
+_EST = {"pairCorrelation": 1, "trimerCorrelationUnDis": 2, "structureFactor": 3, "trimerCorrelation": 4,
+        "trimerCorrelationDis": 5, "trimerhyperRadius": 6, "centerOfMassSquared": 7}
+SCALAR_OBSERVABLES = ("trimerhyperRadius", "centerOfMassSquared")
 
 
 def flatten(cfg):
@@ -181,7 +184,7 @@ def flatten(cfg):
             params += list(w["jastrow"]["coefficients"])
         kind = _WF[w["kind"]]
         sets = [w["set"]] if w["kind"] == "jastrow1b" else w["sets"]
-        if kind == 4:
+        if kind in (4, 5):
             params.append(w.get("hardSphereRadius", -1.0))
         add(1, kind, sets, jk, params)
     for p in cfg.get("potentials", []):
@@ -203,6 +206,8 @@ def flatten(cfg):
         kind = _EST[e["kind"]]
         if kind == 3:
             add(3, kind, e["sets"], e["bins"], [e["maxq"], e["lBox"], e["channel"]])
+        elif kind in (6, 7):      # scalar observables: one "bin" holding the sum
+            add(3, kind, [e["set"]] if kind == 7 else e["sets"], 1, [0.0, 1.0])
         else:
             add(3, kind, e["sets"], e["bins"], [e["minx"], e["maxx"]])
     return np.asarray(ti, dtype=np.int32), np.asarray(tp if tp else [0.0], dtype=np.float64)

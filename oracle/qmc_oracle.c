@@ -425,6 +425,25 @@ static const table *get_table(walker_t *w, int a, int b)
       }                                             \
   }
 
+/* LOOP3B_DIS (dmc/tools3B.h:25-43): i<N1, j<N2, k<N3 ; ij=i*N2+j, jk=j*N3+k, ik=i*N3+k */
+#define ORC_LOOP3B_DIS(N1, N2, N3, BODY)            \
+  {                                                 \
+    int ij = 0, ik2 = 0, ik = 0;                    \
+    for (int i = 0; i < (N1); i++)                  \
+      {                                             \
+        int jk = 0;                                 \
+        for (int j = 0; j < (N2); j++, ij++)        \
+          {                                         \
+            ik = ik2;                               \
+            for (int k = 0; k < (N3); k++, jk++, ik++) \
+              {                                     \
+                BODY                                \
+              }                                     \
+          }                                         \
+        ik2 += (N3);                                \
+      }                                             \
+  }
+
 /* ---- evaluation: productWavefunction::evaluateDerivatives + sumPotentials + energy ------------- */
 typedef struct {
   double logpsi, lap, V, E;
@@ -451,6 +470,19 @@ static int evaluate(const orc_model *m, const double *R, double *grad, eval_out 
       const table *T = get_table(&w, A, A);
       ORC_LOOP3B(N, double rji = T->norm[ji]; double rkj = T->norm[kj]; double rki = T->norm[ki];
                  double Rr = sqrt(rji * rji + rki * rki + rkj * rkj); if (Rr <= hs) valid = 0;)
+    }
+  /* hardSphereConstraintThreeBodyDis (jastrowWavefunctionThreeBody.cpp:54-80) */
+  for (int t = 0; t < m->nTerms && valid; t++)
+    {
+      const int *ti = m->ti + 8 * t;
+      if (ti[0] != 1 || ti[1] != ORC_WF_JASTROW3B_DIS) continue;
+      const double *p = m->tp + ti[7];
+      double hs = p[ti[6] - 1];
+      if (hs < 0) continue;
+      int A = ti[2], B = ti[3], C = ti[4];
+      const table *TAB = get_table(&w, A, B), *TBC = get_table(&w, B, C), *TAC = get_table(&w, A, C);
+      ORC_LOOP3B_DIS(m->N[A], m->N[B], m->N[C], double rij = TAB->norm[ij]; double rjk = TBC->norm[jk]; double rik = TAC->norm[ik];
+                     double Rr = sqrt(rij * rij + rjk * rjk + rik * rik); if (Rr <= hs) valid = 0;)
     }
   if (valid)
     {
@@ -516,6 +548,17 @@ static int evaluate(const orc_model *m, const double *R, double *grad, eval_out 
                            double Rr = sqrt(rji * rji + rki * rki + rkj * rkj); sum += Rr <= p[0] ? v : 0;)
                 break;
               }
+            case ORC_POT_THREEBODY_DIS_SQUAREWELL: /* potentialThreeBody.h:82-108 */
+            case ORC_POT_THREEBODY_DIS_BARRIER:
+              {
+                int A = ti[2], B = ti[3], C = ti[4];
+                const table *TAB = get_table(&w, A, B), *TBC = get_table(&w, B, C), *TAC = get_table(&w, A, C);
+                double v = ti[1] == ORC_POT_THREEBODY_DIS_SQUAREWELL ? -p[1] : p[1];
+                ORC_LOOP3B_DIS(m->N[A], m->N[B], m->N[C], double rij = TAB->norm[ij]; double rjk = TBC->norm[jk];
+                               double rik = TAC->norm[ik]; double Rr = sqrt(rij * rij + rjk * rjk + rik * rik);
+                               sum += Rr <= p[0] ? v : 0;)
+                break;
+              }
             default:
               walker_free(&w);
               return fail("unknown potential kind");
@@ -528,7 +571,7 @@ static int evaluate(const orc_model *m, const double *R, double *grad, eval_out 
           const int *ti = m->ti + 8 * t;
           if (ti[0] != 1) continue;
           radial J;
-          int np = ti[6] - (ti[1] == ORC_WF_JASTROW3B_UNDIS ? 1 : 0);
+          int np = ti[6] - ((ti[1] == ORC_WF_JASTROW3B_UNDIS || ti[1] == ORC_WF_JASTROW3B_DIS) ? 1 : 0);
           if (radial_init(&J, ti[5], m->tp + ti[7], np))
             {
               walker_free(&w);
@@ -605,6 +648,20 @@ static int evaluate(const orc_model *m, const double *R, double *grad, eval_out 
                            g[id * N + k] += tmp1 * (T->diff[id * P + ki] + T->diff[id * P + kj]) / Rr;
                          } laplacian += tmp2 * 3;
                          laplacian += 3 * tmp1 / Rr * (2 * D - 1); waveValue += tmp;)
+            }
+          else if (ti[1] == ORC_WF_JASTROW3B_DIS)
+            { /* jastrowWavefunctionThreeBody.h:222-281 */
+              int A = ti[2], B = ti[3], C = ti[4], NA = m->N[A], NB = m->N[B], NC = m->N[C];
+              const table *TAB = get_table(&w, A, B), *TBC = get_table(&w, B, C), *TAC = get_table(&w, A, C);
+              double *gA = grad + w.off[A], *gB = grad + w.off[B], *gC = grad + w.off[C];
+              ORC_LOOP3B_DIS(NA, NB, NC, double rij = TAB->norm[ij]; double rjk = TBC->norm[jk]; double rik = TAC->norm[ik];
+                             double Rr = sqrt(rij * rij + rjk * rjk + rik * rik); radial_eval(&J, Rr, &tmp, &tmp1, &tmp2);
+                             for (int id = 0; id < D; id++) {
+                               gA[id * NA + i] += tmp1 * (TAB->diff[id * TAB->n + ij] + TAC->diff[id * TAC->n + ik]) / Rr;
+                               gB[id * NB + j] += tmp1 * (-TAB->diff[id * TAB->n + ij] + TBC->diff[id * TBC->n + jk]) / Rr;
+                               gC[id * NC + k] -= tmp1 * (TAC->diff[id * TAC->n + ik] + TBC->diff[id * TBC->n + jk]) / Rr;
+                             } laplacian += tmp2 * 3;
+                             laplacian += 3 * tmp1 / Rr * (2 * D - 1); waveValue += tmp;)
             }
           else
             {
@@ -795,6 +852,70 @@ int orc_histogram_model(const orc_model *m, const double *R, int nW, int iEst, d
           ORC_LOOP3B(N, double rji = T->norm[ji]; double rkj = T->norm[kj]; double rki = T->norm[ki];
                      double radius = sqrt(rji * rji + rki * rki + rkj * rkj);
                      if (radius < maxx) hist_accumulate(sums, minx, dxinv, nf / (radius * radius), radius);)
+          wsum += 1;
+        }
+      else if (ti[1] == ORC_EST_TRIMERCORRELATION)
+        { /* trimerCorrelation.cpp:9-78: set C holds ONE particle; NC = getN(setB) in the normalisation (sic, :64) */
+          double minx = p[0], maxx = p[1], dx = (maxx - minx) / bins, dxinv = 1. / dx;
+          int A = ti[2], B = ti[3], C = ti[4];
+          if (m->N[C] != 1)
+            {
+              walker_free(&w);
+              free(g);
+              return fail("trimerCorrelation: set C must hold one particle");
+            }
+          double NA = m->N[A], NB = m->N[B], NC = m->N[B];
+          double nf = 1 / (dx * 4 * M_PI * NA * NB * NC);
+          const table *T1 = get_table(&w, A, C), *T2 = get_table(&w, B, C), *T3 = get_table(&w, A, B);
+          int N1 = T1->n, N2 = T2->n;
+          for (int i = 0; i < N1; i++)
+            for (int j = 0; j < N2; j++)
+              {
+                double d3 = T3->norm[i * N2 + j];
+                double radius = sqrt(T1->norm[i] * T1->norm[i] + T2->norm[j] * T2->norm[j] + d3 * d3);
+                if (radius < maxx) hist_accumulate(sums, minx, dxinv, nf / (radius * radius), radius);
+              }
+          wsum += 1;
+        }
+      else if (ti[1] == ORC_EST_TRIMERCORRELATION_DIS)
+        { /* trimerCorrelation.cpp:163-227 */
+          double minx = p[0], maxx = p[1], dx = (maxx - minx) / bins, dxinv = 1. / dx;
+          int A = ti[2], B = ti[3], C = ti[4];
+          double NA = m->N[A], NB = m->N[B], NC = m->N[C];
+          double nf = 1 / (dx * 4 * M_PI * NA * NB * NC);
+          const table *TAB = get_table(&w, A, B), *TBC = get_table(&w, B, C), *TAC = get_table(&w, A, C);
+          ORC_LOOP3B_DIS(m->N[A], m->N[B], m->N[C], double rij = TAB->norm[ij]; double rjk = TBC->norm[jk]; double rik = TAC->norm[ik];
+                         double radius = sqrt(rij * rij + rik * rik + rjk * rjk);
+                         if (radius < maxx) hist_accumulate(sums, minx, dxinv, nf / (radius * radius), radius);)
+          wsum += 1;
+        }
+      else if (ti[1] == ORC_EST_TRIMERHYPERRADIUS)
+        { /* hyperRadius.cpp:17-43 (scalar: sums[0] += value, realScalarEstimator / scalarAccumulator accumulators.h:27) */
+          int A = ti[2], B = ti[3], C = ti[4];
+          if (m->N[C] != 1)
+            {
+              walker_free(&w);
+              free(g);
+              return fail("trimerhyperRadius: set C must hold one particle");
+            }
+          const table *T1 = get_table(&w, A, C), *T2 = get_table(&w, B, C), *T3 = get_table(&w, A, B);
+          int N1 = T1->n, N2 = T2->n;
+          double radius = 0;
+          for (int i = 0; i < N1; i++)
+            for (int j = 0; j < N2; j++)
+              {
+                double d3 = T3->norm[i * N2 + j];
+                radius += sqrt(T1->norm[i] * T1->norm[i] + T2->norm[j] * T2->norm[j] + d3 * d3);
+              }
+          sums[0] += radius / (N1 * N2);
+          wsum += 1;
+        }
+      else if (ti[1] == ORC_EST_CENTEROFMASSSQUARED)
+        { /* centerOfMassSquared.cpp:8-18: dis = norm(differencesOneBody(positions,0)); cm = dis.sum()^2 / dis.size() */
+          const table *T = get_table(&w, ti[2], -1);
+          double tot = 0;
+          for (int i = 0; i < T->n; i++) tot += T->norm[i];
+          sums[0] += tot * tot / T->n;
           wsum += 1;
         }
       else if (ti[1] == ORC_EST_STRUCTUREFACTOR)

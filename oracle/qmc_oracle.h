@@ -14,6 +14,7 @@
  *   ti[8*t + 6] = number of parameters,  ti[8*t + 7] = offset of the parameters in tp[]
  * Wavefunction parameters are the JSON-level numbers of the reference constructors (same order
  * as include/qmc4_b200.h documents), followed by hardSphereRadius (or -1) for 3-body terms.
+ * Scalar observables are 1-bin estimators: sums[0] = sum of the observable, weight = walkers (accumulators.h:21-47).
  */
 #ifndef QMC_ORACLE_H
 #define QMC_ORACLE_H
@@ -24,11 +25,12 @@ extern "C" {
 enum { ORC_J_GAUSSIAN = 1, ORC_J_GAUSSGAUSS, ORC_J_SQUAREWELL, ORC_J_HARDSPHEREGAUSS, ORC_J_BSPLINE,
        ORC_J_POSCHTELLER, ORC_J_HARDSPHERE, ORC_J_SQUAREWELL_BOUND,
        ORC_J_DELTA_PHONONS, ORC_J_DELTA_IN_TRAP, ORC_J_DELTA_BOUND_STATE_PHONONS };
-enum { ORC_WF_JASTROW1B = 1, ORC_WF_JASTROW2B_UNDIS, ORC_WF_JASTROW2B_DIS, ORC_WF_JASTROW3B_UNDIS };
+enum { ORC_WF_JASTROW1B = 1, ORC_WF_JASTROW2B_UNDIS, ORC_WF_JASTROW2B_DIS, ORC_WF_JASTROW3B_UNDIS, ORC_WF_JASTROW3B_DIS };
 enum { ORC_POT_HARMONIC1B = 1, ORC_POT_SQUAREWELL2B, ORC_POT_DIPOLAR2B, ORC_POT_POSCHTELLER2B,
        ORC_POT_TWOBODY_SQUAREWELL, ORC_POT_TWOBODY_BARRIER, ORC_POT_THREEBODY_UNDIS_SQUAREWELL,
-       ORC_POT_THREEBODY_UNDIS_BARRIER };
-enum { ORC_EST_PAIRCORRELATION = 1, ORC_EST_TRIMERCORRELATION_UNDIS, ORC_EST_STRUCTUREFACTOR };
+       ORC_POT_THREEBODY_UNDIS_BARRIER, ORC_POT_THREEBODY_DIS_SQUAREWELL, ORC_POT_THREEBODY_DIS_BARRIER };
+enum { ORC_EST_PAIRCORRELATION = 1, ORC_EST_TRIMERCORRELATION_UNDIS, ORC_EST_STRUCTUREFACTOR, ORC_EST_TRIMERCORRELATION,
+       ORC_EST_TRIMERCORRELATION_DIS, ORC_EST_TRIMERHYPERRADIUS /* scalar: bins = 1 */, ORC_EST_CENTEROFMASSSQUARED /* scalar */ };
 
 typedef struct orc_model {
   double lBox[3];

@@ -271,6 +271,15 @@ int ref_histogram(const char * jsonText, const char * scratchDir, const double *
             if (!updateForceGradientEnergy(wk, *m.psi, *m.eO)) continue;
             coll.accumulate(wk, *m.psi);
           }
+        if (auto * sc = dynamic_cast<realScalarEstimator*>(coll[iMeas].get()))
+          { /* scalar observable: scalarAccumulator keeps sum and n private, average() = sum/n (accumulators.h:21-47) */
+            if (bins != 1) throw std::runtime_error("scalar estimator: bins must be 1");
+            auto & acc = sc->getAccumulator();
+            *weight = (double)acc.getWeight();
+            sums[0] = acc.getWeight() > 0 ? acc.average() * (double)acc.getWeight() : 0.;
+            if (chdir(cwd) != 0) throw std::runtime_error("chdir back");
+            return;
+          }
         auto * h = dynamic_cast<realHistogramEstimator*>(coll[iMeas].get());
         if (!h) throw std::runtime_error("measurement is not a histogram estimator");
         auto & acc = h->getAccumulator();
@@ -338,6 +347,15 @@ int ref_forward_walking(const char * jsonText, const char * scratchDir, const do
             for (auto & wk : next) coll.accumulate(wk, *m.psi);
             pop.swap(next);
             off += n[e];
+          }
+        if (auto * sc = dynamic_cast<realScalarForwardWalkingEstimator*>(coll[iEst].get()))
+          { /* scalar observable (correlationEstimator.cpp:36-51): accumulator += record; average() = sum/n */
+            if (bins != 1) throw std::runtime_error("scalar forward-walking estimator: bins must be 1");
+            auto & acc = sc->getAccumulator();
+            *weight = (double)acc.getWeight();
+            sums[0] = acc.getWeight() > 0 ? acc.average() * (double)acc.getWeight() : 0.;
+            if (chdir(cwd) != 0) throw std::runtime_error("chdir back");
+            return;
           }
         auto * h = dynamic_cast<realHistogramForwardWalkingEstimator*>(coll[iEst].get());
         if (!h) throw std::runtime_error("measurement is not a forward-walking histogram estimator");

@@ -344,7 +344,19 @@ int build_plan(qmc_ctx *c)
       D.kind = E.kind;
       D.setA = E.sets[0];
       D.setB = E.sets.size() > 1 ? E.sets[1] : E.sets[0];
+      D.setC = E.sets.size() > 2 ? E.sets[2] : -1;
       if (!set_ok(D.setA) || !set_ok(D.setB)) return fail(c, "estimator: invalid set");
+      const bool three_sets = E.kind == QMC_EST_TRIMERCORRELATION || E.kind == QMC_EST_TRIMERCORRELATION_DIS || E.kind == QMC_EST_TRIMERHYPERRADIUS;
+      if (three_sets)
+        {
+          if (E.sets.size() < 3 || !set_ok(D.setC)) return fail(c, "three-set observable needs sets={A,B,C}");
+          /* asserts of trimerCorrelation.cpp:11,46-47,202 and hyperRadius.cpp:6-7,23 */
+          if (D.setA == D.setB || D.setA == D.setC || D.setB == D.setC) return fail(c, "three-set observable: the sets must be different");
+          if (E.kind != QMC_EST_TRIMERCORRELATION_DIS && P.N[D.setC] != 1)
+            return fail(c, "trimerCorrelation / trimerhyperRadius: set C must hold exactly one particle");
+        }
+      if ((E.kind == QMC_EST_TRIMERHYPERRADIUS || E.kind == QMC_EST_CENTEROFMASSSQUARED) && E.bins != 1)
+        return fail(c, "scalar observable: bins must be 1");
       D.bins = E.bins;
       D.offset = hoff;
       hoff += E.bins;
@@ -362,6 +374,23 @@ int build_plan(qmc_ctx *c)
         { /* trimerCorrelation.cpp:128-143 */
           const double NA = P.N[D.setA];
           D.norm = 1 / (dx * 4 * M_PI * NA * NA * NA);
+        }
+      else if (E.kind == QMC_EST_TRIMERCORRELATION)
+        { /* trimerCorrelation.cpp:58-78: NC = getN(setB) (sic) */
+          const double NA = P.N[D.setA], NB = P.N[D.setB];
+          D.norm = 1 / (dx * 4 * M_PI * NA * NB * NB);
+        }
+      else if (E.kind == QMC_EST_TRIMERCORRELATION_DIS)
+        { /* trimerCorrelation.cpp:209-227 */
+          const double NA = P.N[D.setA], NB = P.N[D.setB], NC = P.N[D.setC];
+          D.norm = 1 / (dx * 4 * M_PI * NA * NB * NC);
+        }
+      else if (E.kind == QMC_EST_TRIMERHYPERRADIUS || E.kind == QMC_EST_CENTEROFMASSSQUARED)
+        {
+          D.norm = 1;
+          D.minx = 0;
+          D.maxx = 1;
+          D.dxinv = 1;
         }
       else if (E.kind == QMC_EST_STRUCTUREFACTOR)
         { /* structureFactor.cpp:8-40 */
@@ -409,6 +438,25 @@ int build_plan(qmc_ctx *c)
           if (P.n3b >= MAX_TRIPLETPASS) return fail(c, "too many triplet passes");
           TripletPass &T = P.p3[P.n3b++];
           T.set = w.sets[0];
+          T.setB = T.setC = -1;
+          T.hist = -1;
+          T.J = w.J;
+          if (w.hs >= 0)
+            {
+              T.has_constraint = 1;
+              T.hs_R0 = w.hs;
+            }
+        }
+      else if (w.kind == QMC_WF_JASTROW3B_DIS)
+        {
+          if (w.sets.size() < 3) return fail(c, "jastrow3bDis needs sets={A,B,C}");
+          if (w.sets[0] == w.sets[1] || w.sets[1] == w.sets[2] || w.sets[0] == w.sets[2])
+            return fail(c, "Sets in three body wavefunction should be distinguishible");   /* jastrowWavefunctionThreeBody.h:173-176 */
+          if (P.n3b >= MAX_TRIPLETPASS) return fail(c, "too many triplet passes");
+          TripletPass &T = P.p3[P.n3b++];
+          T.set = w.sets[0];
+          T.setB = w.sets[1];
+          T.setC = w.sets[2];
           T.hist = -1;
           T.J = w.J;
           if (w.hs >= 0)
@@ -443,18 +491,41 @@ int build_plan(qmc_ctx *c)
         {
           TripletPass *T = nullptr;
           for (int t = 0; t < P.n3b; ++t)
-            if (P.p3[t].set == v.sets[0] && !P.p3[t].has_pot) T = &P.p3[t];
+            if (P.p3[t].setB < 0 && P.p3[t].set == v.sets[0] && !P.p3[t].has_pot) T = &P.p3[t];
           if (!T)
             {
               if (P.n3b >= MAX_TRIPLETPASS) return fail(c, "too many triplet passes");
               T = &P.p3[P.n3b++];
               T->set = v.sets[0];
+              T->setB = T->setC = -1;
               T->hist = -1;
               T->J.kind = J_NONE;
             }
           T->has_pot = 1;
           T->v_R0 = v.p[0];
           T->v_val = (v.kind == QMC_POT_THREEBODY_UNDIS_SQUAREWELL) ? -v.p[1] : v.p[1];   /* potentialFunctors.h:9,26 */
+        }
+      else if (v.kind == QMC_POT_THREEBODY_DIS_SQUAREWELL || v.kind == QMC_POT_THREEBODY_DIS_BARRIER)
+        {
+          if (v.sets.size() < 3) return fail(c, "potentialThreeBodyDis needs sets={A,B,C}");
+          if (v.sets[0] == v.sets[1] || v.sets[1] == v.sets[2] || v.sets[0] == v.sets[2])
+            return fail(c, "Sets in three body wavefunction should be distinguishible");   /* potentialThreeBody.h:68-71 (sic) */
+          TripletPass *T = nullptr;
+          for (int t = 0; t < P.n3b; ++t)   /* same ordered triple: the three pair tables and the loop order coincide */
+            if (P.p3[t].set == v.sets[0] && P.p3[t].setB == v.sets[1] && P.p3[t].setC == v.sets[2] && !P.p3[t].has_pot && !T) T = &P.p3[t];
+          if (!T)
+            {
+              if (P.n3b >= MAX_TRIPLETPASS) return fail(c, "too many triplet passes");
+              T = &P.p3[P.n3b++];
+              T->set = v.sets[0];
+              T->setB = v.sets[1];
+              T->setC = v.sets[2];
+              T->hist = -1;
+              T->J.kind = J_NONE;
+            }
+          T->has_pot = 1;
+          T->v_R0 = v.p[0];
+          T->v_val = (v.kind == QMC_POT_THREEBODY_DIS_SQUAREWELL) ? -v.p[1] : v.p[1];
         }
       else
         {
@@ -518,12 +589,13 @@ int build_plan(qmc_ctx *c)
         {
           TripletPass *T = nullptr;
           for (int t = 0; t < P.n3b; ++t)
-            if (P.p3[t].set == D.setA && P.p3[t].hist < 0 && !T) T = &P.p3[t];
+            if (P.p3[t].setB < 0 && P.p3[t].set == D.setA && P.p3[t].hist < 0 && !T) T = &P.p3[t];
           if (!T)
             {
               if (P.n3b >= MAX_TRIPLETPASS) return fail(c, "too many triplet passes");
               T = &P.p3[P.n3b++];
               T->set = D.setA;
+              T->setB = T->setC = -1;
               T->J.kind = J_NONE;
             }
           T->hist = e;
@@ -561,9 +633,17 @@ int build_plan(qmc_ctx *c)
   int tab = 0;
   for (int t = 0; t < P.n3b; ++t)
     {
-      const int n = P.N[P.p3[t].set];
-      tab = std::max(tab, 2 * (n * (n - 1) / 2));
+      const TripletPass &T = P.p3[t];
+      const int n = P.N[T.set];
+      if (T.setB < 0) tab = std::max(tab, 2 * (n * (n - 1) / 2));
+      else tab = std::max(tab, 2 * (n * P.N[T.setB] + P.N[T.setB] * P.N[T.setC] + n * P.N[T.setC]));
     }
+  for (int e = 0; e < P.nest; ++e)     /* three-set observables build their own r^2 tables (no weights) */
+    if (P.est[e].kind == QMC_EST_TRIMERCORRELATION || P.est[e].kind == QMC_EST_TRIMERCORRELATION_DIS || P.est[e].kind == QMC_EST_TRIMERHYPERRADIUS)
+      {
+        const int a = P.N[P.est[e].setA], b = P.N[P.est[e].setB], cc = P.N[P.est[e].setC];
+        tab = std::max(tab, a * b + b * cc + a * cc);
+      }
   P.needs_pair_table = tab;
   P.aux_doubles = max_sf_bins * 2 * wpw;
   c->max_sf_bins = max_sf_bins;
@@ -959,7 +1039,7 @@ int qmc_add_forward_walking(qmc_ctx *c, int est_index, int record_steps, const i
   if (c->planned) return fail(c, "forward walking must be declared before qmc_set_dmc");
   if (est_index < 0 || est_index >= (int)c->est.size()) return fail(c, "forward walking: estimator index out of range");
   const int kind = c->est[est_index].kind;
-  if (kind != QMC_EST_PAIRCORRELATION && kind != QMC_EST_TRIMERCORRELATION_UNDIS)
+  if (kind == QMC_EST_STRUCTUREFACTOR)
     /* estimatorsFactory.cpp:66-69: only scalar and histogram observables have forward-walking estimators */
     return fail(c, "Forward walking estimator for vector not yet implemented");
   if (record_steps < 1 || n_fw < 1 || !fw_steps) return fail(c, "forward walking: recordSteps and forwardWalkingSteps are required");

@@ -625,6 +625,212 @@ QMC_DEVICE void run_triplet_pass(const Plan &plan, const TripletPass &T, const d
 }
 
 // ---------------------------------------------------------------------------------------------
+// Distinguishable triplet pass on three different sets (A,B,C): jastrow3bDis
+// (jastrowWavefunctionThreeBody.h:170-300), potentialThreeBodyDis (potentialThreeBody.h:62-120),
+// hardSphereConstraintThreeBodyDis (jastrowWavefunctionThreeBody.cpp:54-80); triplets (i in A, j in B,
+// k in C) in LOOP3B_DIS order (tools3B.h:25-43), R^2 = r_ij^2 + r_jk^2 + r_ik^2 from the three
+// minimum-image norms.  Same pair-weight formulation as the undistinguishable pass: the O(NA NB NC)
+// part only produces G^AB_ij = sum_k u'(R)/R, G^BC_jk = sum_i, G^AC_ik = sum_j (three rectangular
+// tables in shared memory next to the r^2 tables), an O(N^2) sweep turns them into gradients:
+//   grad_i += sum_j G^AB_ij d^AB_ij + sum_k G^AC_ik d^AC_ik,   grad_j += -sum_i G^AB_ij d^AB_ij + sum_k G^BC_jk d^BC_jk,
+//   grad_k -= sum_i G^AC_ik d^AC_ik + sum_j G^BC_jk d^BC_jk          (d^XY = min-image(x_X - x_Y), :262-266).
+// Not inlined: it is a cold path that must not weigh on the register allocation of the pair loop.
+struct TripletSums {
+  double lp, lap, V;
+  int invalid;
+};
+
+QMC_DEVICE double dis_r2(const Box &box, const double *xa, int na, int i, const double *xb, int nb, int j)
+{
+  const double dx = min_image(xa[i] - xb[j], box.Lx, box.ix);
+  const double dy = min_image(xa[na + i] - xb[nb + j], box.Ly, box.iy);
+  const double dz = min_image(xa[2 * na + i] - xb[2 * nb + j], box.Lz, box.iz);
+  const double r = sqrt(dx * dx + dy * dy + dz * dz);      /* the reference squares the rounded norms */
+  return r * r;
+}
+
+// r^2 tables of the three rectangular pair tables (A,B), (B,C), (A,C) into tab[0 .. nAB+nBC+nAC)
+QMC_DEVICE void dis_fill_tables(const Plan &plan, const TripletPass &T, const Scratch &S, const Group &G, double *tab)
+{
+  const Box box = {plan.L[0], plan.L[1], plan.L[2], plan.Linv[0], plan.Linv[1], plan.Linv[2]};
+  const int nA = plan.N[T.set], nB = plan.N[T.setB], nC = plan.N[T.setC];
+  const double *xA = S.R + plan.off[T.set], *xB = S.R + plan.off[T.setB], *xC = S.R + plan.off[T.setC];
+  const int nAB = nA * nB, nBC = nB * nC, nAC = nA * nC;
+  for (int k = G.gtid; k < nAB + nBC + nAC; k += G.gsize)
+    {
+      if (k < nAB) tab[k] = dis_r2(box, xA, nA, k / nB, xB, nB, k % nB);
+      else if (k < nAB + nBC) tab[k] = dis_r2(box, xB, nB, (k - nAB) / nC, xC, nC, (k - nAB) % nC);
+      else tab[k] = dis_r2(box, xA, nA, (k - nAB - nBC) / nC, xC, nC, (k - nAB - nBC) % nC);
+    }
+}
+
+// Scratch and Group cross the call BY VALUE, member by member: taking their address in the caller would push
+// them to local memory and the pair loop would lose the shared-memory address space of S.R (LD instead of LDS).
+struct ColdArgs {
+  double *R, *acc, *red, *tab;
+  int gtid, gsize, gwarp, nwarps, lane, bar_id;
+};
+QMC_DEVICE ColdArgs cold_args(const Scratch &S, const Group &G)
+{
+  ColdArgs a = {S.R, S.acc, S.red, S.tab, G.gtid, G.gsize, G.gwarp, G.nwarps, G.lane, G.bar_id};
+  return a;
+}
+QMC_DEVICE void cold_unpack(const ColdArgs &a, Scratch &S, Group &G)
+{
+  S.R = a.R;
+  S.acc = a.acc;
+  S.red = a.red;
+  S.tab = a.tab;
+  S.aux = nullptr;
+  G.gtid = a.gtid;
+  G.gsize = a.gsize;
+  G.gwarp = a.gwarp;
+  G.nwarps = a.nwarps;
+  G.lane = a.lane;
+  G.bar_id = a.bar_id;
+}
+
+static __device__ QMC_NOINLINE TripletSums run_triplet_pass_dis(const Plan &plan, int t, const double *coef, ColdArgs ca)
+{
+  const TripletPass &T = plan.p3[t];
+  Scratch S;
+  Group G;
+  cold_unpack(ca, S, G);
+  TripletSums out = {0.0, 0.0, 0.0, 0};
+  const Box box = {plan.L[0], plan.L[1], plan.L[2], plan.Linv[0], plan.Linv[1], plan.Linv[2]};
+  const int nA = plan.N[T.set], nB = plan.N[T.setB], nC = plan.N[T.setC];
+  const double *xA = S.R + plan.off[T.set], *xB = S.R + plan.off[T.setB], *xC = S.R + plan.off[T.setC];
+  const int nAB = nA * nB, nBC = nB * nC, nAC = nA * nC, nT = nAB + nBC + nAC;
+  double *r2AB = S.tab, *r2BC = r2AB + nAB, *r2AC = r2BC + nBC;
+  double *gAB = S.tab + nT, *gBC = gAB + nAB, *gAC = gBC + nBC;
+  const bool hasJ = T.J.kind != J_NONE;
+  dis_fill_tables(plan, T, S, G, S.tab);
+  G.sync();
+  // (i,j) owners: scalars once per triplet + G^AB
+  for (int p = G.gtid; p < nAB; p += G.gsize)
+    {
+      const int i = p / nB, j = p - i * nB;
+      const double rij2 = r2AB[p];
+      double g = 0;
+      for (int k = 0; k < nC; ++k)
+        {
+          const double R = sqrt(rij2 + r2BC[j * nC + k] + r2AC[i * nC + k]);
+          double d0 = 0, d1 = 0, d2 = 0;
+          if (hasJ) eval_radial(T.J, coef, R, d0, d1, d2);
+          g += d1 / R;
+          out.lp += d0;
+          out.lap += d2 * 3 + 3 * d1 / R * 5;      /* (2D-1) = 5 */
+          if (T.has_pot && R <= T.v_R0) out.V += T.v_val;
+          if (T.has_constraint && R <= T.hs_R0) out.invalid = 1;
+        }
+      gAB[p] = g;
+    }
+  if (hasJ)
+    {
+      for (int p = G.gtid; p < nBC + nAC; p += G.gsize)
+        {
+          double g = 0;
+          if (p < nBC)
+            {
+              const int j = p / nC, k = p - j * nC;
+              for (int i = 0; i < nA; ++i)
+                {
+                  const double R = sqrt(r2AB[i * nB + j] + r2BC[p] + r2AC[i * nC + k]);
+                  double d0, d1, d2;
+                  eval_radial(T.J, coef, R, d0, d1, d2);
+                  g += d1 / R;
+                }
+              gBC[p] = g;
+            }
+          else
+            {
+              const int q = p - nBC, i = q / nC, k = q - i * nC;
+              for (int j = 0; j < nB; ++j)
+                {
+                  const double R = sqrt(r2AB[i * nB + j] + r2BC[j * nC + k] + r2AC[q]);
+                  double d0, d1, d2;
+                  eval_radial(T.J, coef, R, d0, d1, d2);
+                  g += d1 / R;
+                }
+              gAC[q] = g;
+            }
+        }
+      G.sync();
+      double *accw = S.acc + (size_t)G.gwarp * plan.dofs;
+      double *aA = accw + plan.off[T.set], *aB = accw + plan.off[T.setB], *aC = accw + plan.off[T.setC];
+      for (int p = G.gtid; p < nA + nB + nC; p += G.gsize)
+        {
+          double gx = 0, gy = 0, gz = 0;
+          if (p < nA)
+            {
+              const int i = p;
+              for (int j = 0; j < nB; ++j)
+                {
+                  const double w = gAB[i * nB + j];
+                  gx = fma(w, min_image(xA[i] - xB[j], box.Lx, box.ix), gx);
+                  gy = fma(w, min_image(xA[nA + i] - xB[nB + j], box.Ly, box.iy), gy);
+                  gz = fma(w, min_image(xA[2 * nA + i] - xB[2 * nB + j], box.Lz, box.iz), gz);
+                }
+              for (int k = 0; k < nC; ++k)
+                {
+                  const double w = gAC[i * nC + k];
+                  gx = fma(w, min_image(xA[i] - xC[k], box.Lx, box.ix), gx);
+                  gy = fma(w, min_image(xA[nA + i] - xC[nC + k], box.Ly, box.iy), gy);
+                  gz = fma(w, min_image(xA[2 * nA + i] - xC[2 * nC + k], box.Lz, box.iz), gz);
+                }
+              aA[i] += gx;
+              aA[nA + i] += gy;
+              aA[2 * nA + i] += gz;
+            }
+          else if (p < nA + nB)
+            {
+              const int j = p - nA;
+              for (int i = 0; i < nA; ++i)
+                {
+                  const double w = -gAB[i * nB + j];
+                  gx = fma(w, min_image(xA[i] - xB[j], box.Lx, box.ix), gx);
+                  gy = fma(w, min_image(xA[nA + i] - xB[nB + j], box.Ly, box.iy), gy);
+                  gz = fma(w, min_image(xA[2 * nA + i] - xB[2 * nB + j], box.Lz, box.iz), gz);
+                }
+              for (int k = 0; k < nC; ++k)
+                {
+                  const double w = gBC[j * nC + k];
+                  gx = fma(w, min_image(xB[j] - xC[k], box.Lx, box.ix), gx);
+                  gy = fma(w, min_image(xB[nB + j] - xC[nC + k], box.Ly, box.iy), gy);
+                  gz = fma(w, min_image(xB[2 * nB + j] - xC[2 * nC + k], box.Lz, box.iz), gz);
+                }
+              aB[j] += gx;
+              aB[nB + j] += gy;
+              aB[2 * nB + j] += gz;
+            }
+          else
+            {
+              const int k = p - nA - nB;
+              for (int i = 0; i < nA; ++i)
+                {
+                  const double w = -gAC[i * nC + k];
+                  gx = fma(w, min_image(xA[i] - xC[k], box.Lx, box.ix), gx);
+                  gy = fma(w, min_image(xA[nA + i] - xC[nC + k], box.Ly, box.iy), gy);
+                  gz = fma(w, min_image(xA[2 * nA + i] - xC[2 * nC + k], box.Lz, box.iz), gz);
+                }
+              for (int j = 0; j < nB; ++j)
+                {
+                  const double w = -gBC[j * nC + k];
+                  gx = fma(w, min_image(xB[j] - xC[k], box.Lx, box.ix), gx);
+                  gy = fma(w, min_image(xB[nB + j] - xC[nC + k], box.Ly, box.iy), gy);
+                  gz = fma(w, min_image(xB[2 * nB + j] - xC[2 * nC + k], box.Lz, box.iz), gz);
+                }
+              aC[k] += gx;
+              aC[nC + k] += gy;
+              aC[2 * nC + k] += gz;
+            }
+        }
+    }
+  G.sync();
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
 // One-body terms: jastrow1b (jastrowWavefunctionOneBody.h:53-85; laplacian has NO factor 2) and
 // harmonic1b (potential.cpp:21-32).  The "distance from the origin" is minimum-imaged too
 // (geometry.cpp:9-25).
@@ -677,7 +883,18 @@ QMC_DEVICE EvalResult evaluate_walker(const Plan &plan, const double *coef, cons
   if (plan.n3b > 0)
     {
       G.sync();
-      for (int t = 0; t < plan.n3b; ++t) run_triplet_pass(plan, plan.p3[t], coef, S, G, H, lp, lap, V, invalid);
+      for (int t = 0; t < plan.n3b; ++t)
+        {
+          if (plan.p3[t].setB < 0) run_triplet_pass(plan, plan.p3[t], coef, S, G, H, lp, lap, V, invalid);
+          else
+            {
+              const TripletSums ts = run_triplet_pass_dis(plan, t, coef, cold_args(S, G));
+              lp += ts.lp;
+              lap += ts.lap;
+              V += ts.V;
+              invalid |= ts.invalid;
+            }
+        }
     }
   // scalar reduction: warp shuffle, then fixed-order sum over the group's warps
   lp = warp_sum(lp);
@@ -909,6 +1126,98 @@ QMC_DEVICE void hist_fx_flush(const Plan &plan, unsigned *fx, double *replica)
     }
 }
 
+// Three-set observables on the FINAL configuration (cold path, not inlined): trimerCorrelation
+// (trimerCorrelation.cpp:9-41, set C holds one particle), trimerCorrelationDis (:163-199) and the scalar
+// trimerhyperRadius (hyperRadius.cpp:17-43: mean of R over the (i,j) pairs).  The order of the three
+// squared norms under the square root follows each reference routine, so bins match bit for bit.
+static __device__ QMC_NOINLINE void post_three_set_observable(const Plan &plan, int e, ColdArgs ca, double *replica, double w)
+{
+  const Estimator &est = plan.est[e];
+  Scratch S;
+  Group G;
+  cold_unpack(ca, S, G);
+  TripletPass T;
+  T.set = est.setA;
+  T.setB = est.setB;
+  T.setC = est.setC;
+  const int nA = plan.N[T.set], nB = plan.N[T.setB], nC = plan.N[T.setC];
+  const int nAB = nA * nB, nBC = nB * nC;
+  const double *r2AB = S.tab, *r2BC = r2AB + nAB, *r2AC = r2BC + nBC;
+  G.sync();
+  dis_fill_tables(plan, T, S, G, S.tab);
+  G.sync();
+  if (est.kind == 6 /* QMC_EST_TRIMERHYPERRADIUS */)
+    {
+      double sum = 0;
+      for (int p = G.gtid; p < nAB; p += G.gsize)
+        {
+          const int i = p / nB, j = p - i * nB;
+          sum += sqrt(r2AC[i] + r2BC[j] + r2AB[p]);
+        }
+      sum = warp_sum(sum);
+      if (G.lane == 0) S.red[G.gwarp * 4] = sum;
+      G.sync();
+      if (G.gtid == 0)
+        {
+          double tot = 0;
+          for (int q = 0; q < G.nwarps; ++q) tot += S.red[q * 4];
+          atomicAdd(replica + est.offset, w * (tot / (double)(nA * nB)));
+        }
+    }
+  else
+    {
+      double *hist = replica + est.offset;
+      const double hw = w * est.norm;
+      const bool plain = est.kind == 4 /* QMC_EST_TRIMERCORRELATION */;
+      for (int p = G.gtid; p < nAB; p += G.gsize)
+        {
+          const int i = p / nB, j = p - i * nB;
+          for (int k = 0; k < nC; ++k)
+            {
+              const double ab = r2AB[p], bc = r2BC[j * nC + k], ac = r2AC[i * nC + k];
+              const double R = plain ? sqrt(ac + bc + ab) : sqrt(ab + ac + bc);
+              if (R < est.maxx)
+                {
+                  const int bin = (int)((R - est.minx) * est.dxinv);
+                  if (bin >= 0) atomicAdd(hist + min(bin, est.bins - 1), hw / (R * R));
+                }
+            }
+        }
+    }
+  G.sync();
+}
+
+// centerOfMassSquared (centerOfMassSquared.cpp:8-18): (sum_i |r_i|)^2 / N with the minimum-imaged distance
+// from the origin (geometry.cpp:9-25) — the reference's definition, not the centre of mass.
+static __device__ QMC_NOINLINE void post_center_of_mass_squared(const Plan &plan, int e, ColdArgs ca, double *replica, double w)
+{
+  const Estimator &est = plan.est[e];
+  Scratch S;
+  Group G;
+  cold_unpack(ca, S, G);
+  const int n = plan.N[est.setA];
+  const double *x = S.R + plan.off[est.setA];
+  double sum = 0;
+  for (int i = G.gtid; i < n; i += G.gsize)
+    {
+      const double dx = min_image(x[i], plan.L[0], plan.Linv[0]);
+      const double dy = min_image(x[n + i], plan.L[1], plan.Linv[1]);
+      const double dz = min_image(x[2 * n + i], plan.L[2], plan.Linv[2]);
+      sum += sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  sum = warp_sum(sum);
+  G.sync();
+  if (G.lane == 0) S.red[G.gwarp * 4] = sum;
+  G.sync();
+  if (G.gtid == 0)
+    {
+      double tot = 0;
+      for (int q = 0; q < G.nwarps; ++q) tot += S.red[q * 4];
+      atomicAdd(replica + est.offset, w * (tot * tot / (double)n));
+    }
+  G.sync();
+}
+
 // Estimators that are evaluated on the FINAL configuration (in S.R) with its branching weight:
 // trimerCorrelationUnDis (trimerCorrelation.cpp:82-143) and the structure factor
 // (structureFactor.cpp:56-90 applied to coordinate 0; q_j = q0 + j*dq, structureFactor.cpp:23-40).
@@ -918,7 +1227,7 @@ QMC_DEVICE void post_estimators(const Plan &plan, const Scratch &S, const Group 
   for (int t = 0; t < plan.n3b; ++t)
     {
       const TripletPass &T = plan.p3[t];
-      if (T.hist < 0) continue;
+      if (T.hist < 0 || T.setB >= 0) continue;
       const Estimator &est = plan.est[T.hist];
       double *hist = H.base + est.offset;
       const double hw = H.w * est.norm;
@@ -957,6 +1266,12 @@ QMC_DEVICE void post_estimators(const Plan &plan, const Scratch &S, const Group 
             }
         }
       G.sync();
+    }
+  for (int e = 0; e < plan.nest; ++e)
+    {
+      const Estimator &est = plan.est[e];
+      if (est.kind >= 4 && est.kind <= 6) post_three_set_observable(plan, e, cold_args(S, G), H.base, H.w);
+      else if (est.kind == 7 /* QMC_EST_CENTEROFMASSSQUARED */) post_center_of_mass_squared(plan, e, cold_args(S, G), H.base, H.w);
     }
   for (int e = 0; e < plan.nest; ++e)
     {

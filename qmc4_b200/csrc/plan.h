@@ -10,8 +10,8 @@ namespace qmc {
 constexpr int MAX_SPECIES = 4;
 constexpr int MAX_ONEBODY = 4;
 constexpr int MAX_PAIRPASS = 4;
-constexpr int MAX_TRIPLETPASS = 2;
-constexpr int MAX_EST = 4;
+constexpr int MAX_TRIPLETPASS = 3;
+constexpr int MAX_EST = 6;
 constexpr int NJP = 16;   // derived parameters per radial functor
 
 // radial functor kinds as evaluated on the device (qmc_jastrow_kind + NONE)
@@ -47,11 +47,13 @@ struct PairPass {          // one fused pass over the (setA,setB) pair table
   RadialFn J;              // J_NONE if the pass only carries a potential / estimator
 };
 
-struct TripletPass {       // jastrow3bUnDis + potentialThreeBodyUnDis + trimerCorrelationUnDis on set A
-  int set;
+struct TripletPass {       // jastrow3bUnDis + potentialThreeBodyUnDis + trimerCorrelationUnDis on set A, or their
+                           // distinguishable versions (jastrow3bDis, potentialThreeBodyDis, trimerCorrelation{,Dis}) on (A,B,C)
+  int set;                 // A
   int has_pot;
   int hist;                // index into Plan::est or -1
   int has_constraint;
+  int setB, setC;          // -1: undistinguishable pass on `set`; else three different sets (LOOP3B_DIS, tools3B.h:25-43)
   double v_R0, v_val;      // F(R) = R<=R0 ? v_val : 0
   double hs_R0;            // hardSphereConstraintThreeBodyUnDis: invalid if any R <= hs_R0
   RadialFn J;              // may be J_NONE
@@ -63,6 +65,8 @@ struct Estimator {
   int bins;
   int offset;              // offset (doubles) of this estimator's sums inside one histogram replica
   int channel;             // structureFactor
+  int setC;                // three-set observables (trimerCorrelation, trimerCorrelationDis, trimerhyperRadius)
+  int pad;
   double minx, maxx, dxinv;
   double norm;             // pairCorrelation.cpp:41-59 / trimerCorrelation.cpp:128-143 normalisation factor
   double q0, dq;           // structureFactor q-grid (structureFactor.cpp:8-40)

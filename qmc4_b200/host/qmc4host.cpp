@@ -53,6 +53,22 @@ int trimerCorrelationUnDis::emit(qmc_ctx *ctx, int bins, real_t minx, real_t max
   rethrow(ctx, qmc_add_estimator(ctx, QMC_EST_TRIMERCORRELATION_UNDIS, &setA, 1, bins, minx, maxx, nullptr, 0, &idx));
   return idx;
 }
+template <int EST_KIND, bool SCALAR> int threeSetObservable<EST_KIND, SCALAR>::emit(qmc_ctx *ctx, int bins, real_t minx, real_t maxx) const
+{
+  int idx = -1;
+  const int s[3] = {setA, setB, setC};
+  rethrow(ctx, qmc_add_estimator(ctx, EST_KIND, s, 3, SCALAR ? 1 : bins, minx, maxx, nullptr, 0, &idx));
+  return idx;
+}
+template class threeSetObservable<QMC_EST_TRIMERCORRELATION, false>;
+template class threeSetObservable<QMC_EST_TRIMERCORRELATION_DIS, false>;
+template class threeSetObservable<QMC_EST_TRIMERHYPERRADIUS, true>;
+int centerOfMassSquared::emit(qmc_ctx *ctx, int, real_t, real_t) const
+{
+  int idx = -1;
+  rethrow(ctx, qmc_add_estimator(ctx, QMC_EST_CENTEROFMASSSQUARED, &setA, 1, 1, 0, 1, nullptr, 0, &idx));
+  return idx;
+}
 std::vector<real_t> structureFactor::x(int n) const
 { /* build_q_vector (structureFactor.cpp:8-40) */
   double dq = int(maxq / (2 * M_PI * n / lBox)) * 2 * M_PI / lBox;
@@ -98,6 +114,17 @@ void estimatorBase::dump()
 realScalarEstimator::realScalarEstimator(const std::string &label) : estimatorBase(label) { headerIfEmpty(label); }
 void realScalarEstimator::write(std::ostream &stream)
 {
+  stream << std::scientific << std::setprecision(12);
+  if (n > 0) stream << sum / n;
+}
+realScalarObservableEstimator::realScalarObservableEstimator(observableBase *ob_, const json_t &j)
+    : estimatorBase(j["label"].get<std::string>()), ob(ob_)
+{
+  headerIfEmpty(_label);                               /* estimators.cpp:35-46 */
+}
+void realScalarObservableEstimator::collect(qmc_ctx *ctx, const qmc_block_result &) { rethrow(ctx, qmc_get_estimator(ctx, index, &sum, 1, &n)); }
+void realScalarObservableEstimator::write(std::ostream &stream)
+{ /* realScalarEstimator::write (estimators.cpp:89-98) */
   stream << std::scientific << std::setprecision(12);
   if (n > 0) stream << sum / n;
 }
@@ -151,6 +178,17 @@ void realHistogramForwardWalkingEstimator::write(std::ostream &stream)
   for (size_t i = 0; i < sums.size(); i++) stream << group->minx + (i + 0.5) * dx << " " << sums[i] / weight << std::endl;
 }
 
+realScalarForwardWalkingEstimator::realScalarForwardWalkingEstimator(std::shared_ptr<forwardWalkingGroup> g, int k_, const std::string &label)
+    : estimatorBase(label), group(g), k(k_)
+{
+  headerIfEmpty(_label);                               /* correlationEstimator.cpp:53-66 */
+}
+void realScalarForwardWalkingEstimator::collect(qmc_ctx *ctx, const qmc_block_result &) { rethrow(ctx, qmc_get_estimator(ctx, group->first + k, &sum, 1, &n)); }
+void realScalarForwardWalkingEstimator::write(std::ostream &stream)
+{ /* correlationEstimator.cpp:73-80: default stream formatting (no std::scientific here in the reference) */
+  if (n > 0) stream << sum / n;
+}
+
 // ---- factory ---------------------------------------------------------------------------------------------
 factory &getFactory()
 {
@@ -173,6 +211,10 @@ void registerDefaults(factory &f)
   f.registerObservable<pairCorrelation>();
   f.registerObservable<trimerCorrelationUnDis>();
   f.registerObservable<structureFactor>();
+  f.registerObservable<centerOfMassSquared>();               /* main.cpp:203-207 */
+  f.registerObservable<trimerhyperRadius>();
+  f.registerObservable<trimerCorrelation>();
+  f.registerObservable<trimerCorrelationDis>();
   f.registerPotential<harmonicPotential>();
   f.registerPotential<squareWellPotential2b>();
   f.registerPotential<dipolarPotential2b>();
@@ -219,21 +261,28 @@ std::vector<estimatorBase *> factory::createEstimators(const json_t &j)
           if (g->ob->isVector()) throw missingImplementation("Forward walking estimator for vector not yet implemented");
           if (!e.contains("recordSteps") || e["recordSteps"].get<int>() <= 0)
             throw invalidInput("forwardWalkingSteps needs recordSteps > 0 on the same measurement (the storer, estimatorsFactory.h:112-121)");
-          g->bins = e["bins"].get<int>();
-          g->minx = e["minx"].get<real_t>();
-          g->maxx = e["maxx"].get<real_t>();
+          const bool scalar = g->ob->isScalar();
+          g->bins = scalar ? 1 : e["bins"].get<int>();
+          g->minx = scalar ? 0 : e["minx"].get<real_t>();
+          g->maxx = scalar ? 1 : e["maxx"].get<real_t>();
           g->recordSteps = e["recordSteps"].get<int>();
           for (const json_t &st : e["forwardWalkingSteps"].elements()) g->steps.push_back(st.get<int>());
           const std::string label = e["label"].get<std::string>();
           for (size_t k = 0; k < g->steps.size(); k++)
-            out.push_back(new realHistogramForwardWalkingEstimator(g, (int)k, label + "_fw" + std::to_string(g->steps[k])));
+            {
+              const std::string lk = label + "_fw" + std::to_string(g->steps[k]);
+              if (scalar) out.push_back(new realScalarForwardWalkingEstimator(g, (int)k, lk));      /* estimatorsFactory.cpp:60-63 */
+              else out.push_back(new realHistogramForwardWalkingEstimator(g, (int)k, lk));
+            }
           continue;
         }
       if (id == "superfluidFraction") throw missingImplementation("superfluidFraction is not on the GPU path yet");
       if (id == "forceEnergy" || id == "energy") continue;
       auto it = obs.find(id);
       if (it == obs.end()) throw factoryIdNotRecorded(id);
-      out.push_back(new realHistogramEstimator(it->second(e), e));
+      observableBase *ob = it->second(e);
+      if (ob->isScalar()) out.push_back(new realScalarObservableEstimator(ob, e));
+      else out.push_back(new realHistogramEstimator(ob, e));
     }
   return out;
 }

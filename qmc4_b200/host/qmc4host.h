@@ -180,6 +180,24 @@ template <class jastrow_t> class jastrowThreeBodyWavefunctionUnDistinguishable :
   real_t hs;
 };
 
+template <class jastrow_t> class jastrowThreeBodyWavefunctionDistinguishable : public wavefunction {   // jastrowWavefunctionThreeBody.h:164-305
+ public:
+  jastrowThreeBodyWavefunctionDistinguishable(const json_t &j, const geometry_t &geo)
+      : wavefunction(geo), J(j["jastrow"]), setA(j["sets"][0].get<int>()), setB(j["sets"][1].get<int>()), setC(j["sets"][2].get<int>()),
+        hs(j.contains("hardSphereRadius") ? j["hardSphereRadius"].get<real_t>() : -1)
+  {
+    if (setA == setB || setB == setC || setA == setC) throw invalidInput("Sets in three body wavefunction should be distinguishible");
+  }
+  static std::string name() { return "jastrow3bDis/" + jastrow_t::name(); }
+  std::vector<int> sets() const override { return {setA, setB, setC}; }
+  void emit(qmc_ctx *ctx) const override { add(ctx, QMC_WF_JASTROW3B_DIS, {setA, setB, setC}, J, hs); }
+
+ private:
+  jastrow_t J;
+  int setA, setB, setC;
+  real_t hs;
+};
+
 class productWavefunction {
  public:
   productWavefunction() {}
@@ -243,6 +261,7 @@ struct squareWell {        // potentialFunctors.h:5-19
   static std::string name() { return "squareWell"; }
   static int kind2b() { return QMC_POT_TWOBODY_SQUAREWELL; }
   static int kind3b() { return QMC_POT_THREEBODY_UNDIS_SQUAREWELL; }
+  static int kind3bDis() { return QMC_POT_THREEBODY_DIS_SQUAREWELL; }
   real_t R0, V0;
 };
 struct potentialBarrier {  // potentialFunctors.h:22-36
@@ -250,6 +269,7 @@ struct potentialBarrier {  // potentialFunctors.h:22-36
   static std::string name() { return "potentialBarrier"; }
   static int kind2b() { return QMC_POT_TWOBODY_BARRIER; }
   static int kind3b() { return QMC_POT_THREEBODY_UNDIS_BARRIER; }
+  static int kind3bDis() { return QMC_POT_THREEBODY_DIS_BARRIER; }
   real_t R0, V0;
 };
 template <class functor_t> class potentialTwoBody : public potential {      // potentialTwoBody.h
@@ -275,6 +295,22 @@ template <class functor_t> class potentialThreeBodyUnDis : public potential {   
   int setA;
 };
 
+template <class functor_t> class potentialThreeBodyDis : public potential {     // potentialThreeBody.h:60-125
+ public:
+  potentialThreeBodyDis(const json_t &j, const geometry_t &geo)
+      : potential(geo), V(j["functor"]), setA(j["sets"][0].get<int>()), setB(j["sets"][1].get<int>()), setC(j["sets"][2].get<int>())
+  {
+    if (setA == setB || setB == setC || setA == setC) throw invalidInput("Sets in three body wavefunction should be distinguishible");   /* sic, :70 */
+  }
+  static std::string name() { return "potentialThreeBodyDis/" + functor_t::name(); }
+  std::vector<int> sets() const override { return {setA, setB, setC}; }
+  void emit(qmc_ctx *ctx) const override { add(ctx, functor_t::kind3bDis(), {setA, setB, setC}, {V.R0, V.V0}); }
+
+ private:
+  functor_t V;
+  int setA, setB, setC;
+};
+
 class sumPotentials {
  public:
   explicit sumPotentials(std::vector<potential *> p) : _potentials(p) {}
@@ -292,7 +328,43 @@ struct observableBase {
   virtual int emit(qmc_ctx *ctx, int bins, real_t minx, real_t maxx) const = 0;   // returns the device estimator index
   virtual std::vector<int> sets() const = 0;
   virtual bool isVector() const { return false; }
+  virtual bool isScalar() const { return false; }        // realScalarObservable (observables.h:10-30)
   virtual std::vector<real_t> x(int) const { return {}; }
+};
+// observables over three sets: trimerCorrelation (set C = one impurity, trimerCorrelation.cpp:9-78), trimerCorrelationDis
+// (:163-227) are histograms; trimerhyperRadius (hyperRadius.cpp) is a scalar
+template <int EST_KIND, bool SCALAR> class threeSetObservable : public observableBase {
+ public:
+  explicit threeSetObservable(const json_t &j) : setA(j["sets"][0].get<int>()), setB(j["sets"][1].get<int>()), setC(j["sets"][2].get<int>()) {}
+  std::vector<int> sets() const override { return {setA, setB, setC}; }
+  bool isScalar() const override { return SCALAR; }
+  int emit(qmc_ctx *ctx, int bins, real_t minx, real_t maxx) const override;
+
+ private:
+  int setA, setB, setC;
+};
+struct trimerCorrelation : threeSetObservable<QMC_EST_TRIMERCORRELATION, false> {
+  using threeSetObservable::threeSetObservable;
+  static std::string name() { return "trimerCorrelation"; }
+};
+struct trimerCorrelationDis : threeSetObservable<QMC_EST_TRIMERCORRELATION_DIS, false> {
+  using threeSetObservable::threeSetObservable;
+  static std::string name() { return "trimerCorrelationDis"; }
+};
+struct trimerhyperRadius : threeSetObservable<QMC_EST_TRIMERHYPERRADIUS, true> {
+  using threeSetObservable::threeSetObservable;
+  static std::string name() { return "trimerhyperRadius"; }
+};
+class centerOfMassSquared : public observableBase {             // centerOfMassSquared.cpp:6 ("set", not "sets")
+ public:
+  explicit centerOfMassSquared(const json_t &j) : setA(j["set"].get<int>()) {}
+  static std::string name() { return "centerOfMassSquared"; }
+  std::vector<int> sets() const override { return {setA}; }
+  bool isScalar() const override { return true; }
+  int emit(qmc_ctx *ctx, int bins, real_t minx, real_t maxx) const override;
+
+ private:
+  int setA;
 };
 class pairCorrelation : public observableBase {                 // pairCorrelation.cpp:9-15
  public:
@@ -359,6 +431,19 @@ class realScalarEstimator : public estimatorBase {              // the implicit 
  private:
   real_t sum = 0, n = 0;
 };
+class realScalarObservableEstimator : public estimatorBase {    // realScalarEstimator(ob, j) (estimators.cpp:48): reads "label" only
+ public:
+  realScalarObservableEstimator(observableBase *ob, const json_t &j);
+  void registerOn(qmc_ctx *ctx) override { index = ob->emit(ctx, 1, 0, 1); }
+  void collect(qmc_ctx *ctx, const qmc_block_result &) override;
+  void write(std::ostream &stream) override;
+  std::vector<int> sets() const override { return ob->sets(); }
+
+ private:
+  std::unique_ptr<observableBase> ob;
+  real_t sum = 0, n = 0;
+  int index = -1;
+};
 class realHistogramEstimator : public estimatorBase {           // estimators.cpp:50-87
  public:
   realHistogramEstimator(observableBase *ob, const json_t &j);
@@ -401,6 +486,19 @@ class realHistogramForwardWalkingEstimator : public estimatorBase {
   real_t weight = 0;
 };
 
+class realScalarForwardWalkingEstimator : public estimatorBase {   // correlationEstimator.cpp:36-80
+ public:
+  realScalarForwardWalkingEstimator(std::shared_ptr<forwardWalkingGroup> group, int k, const std::string &label);
+  void registerOn(qmc_ctx *ctx) override { group->ensureRegistered(ctx); }
+  void collect(qmc_ctx *ctx, const qmc_block_result &) override;
+  void write(std::ostream &stream) override;
+
+ private:
+  std::shared_ptr<forwardWalkingGroup> group;
+  int k;
+  real_t sum = 0, n = 0;
+};
+
 // ---- factory (dmc/factory.h) -------------------------------------------------------------------------
 class factory {
  public:
@@ -420,6 +518,7 @@ class factory {
   {
     registerPotential<potentialTwoBody<functor_t> >();
     registerPotential<potentialThreeBodyUnDis<functor_t> >();
+    registerPotential<potentialThreeBodyDis<functor_t> >();
   }
   template <class jastrow_t> void registerJastrow()
   { /* one call registers the Jastrow for every wavefunction template (factory.h:50-60) */
@@ -427,6 +526,7 @@ class factory {
     registerWavefunction<jastrowTwoBodyWavefunctionUndistinguishable<jastrow_t> >();
     registerWavefunction<jastrowTwoBodyWavefunctionDistinguishable<jastrow_t> >();
     registerWavefunction<jastrowThreeBodyWavefunctionUnDistinguishable<jastrow_t> >();
+    registerWavefunction<jastrowThreeBodyWavefunctionDistinguishable<jastrow_t> >();
   }
   template <class ob_t> void registerObservable()
   {

@@ -76,7 +76,8 @@ _JASTROWS = {
     "delta_bound_state_phonons": (capi.J_DELTA_BOUND_STATE_PHONONS, lambda j: _delta_bound_state(j)),
 }
 _WAVES = {"jastrow1b": capi.WF_JASTROW1B, "jastrow2bUnDis": capi.WF_JASTROW2B_UNDIS,
-          "jastrow2bDis": capi.WF_JASTROW2B_DIS, "jastrow3bUnDis": capi.WF_JASTROW3B_UNDIS}
+          "jastrow2bDis": capi.WF_JASTROW2B_DIS, "jastrow3bUnDis": capi.WF_JASTROW3B_UNDIS,
+          "jastrow3bDis": capi.WF_JASTROW3B_DIS}
 _POTENTIALS = {
     "harmonic1b": (capi.POT_HARMONIC1B, lambda j: ([_get(j, "set")], [_get(j, "omega")])),
     "squareWell2b": (capi.POT_SQUAREWELL2B, lambda j: (_get(j, "sets"), [_get(j, "V0"), _get(j, "R0")])),
@@ -86,7 +87,14 @@ _POTENTIALS = {
     "potentialTwoBody/potentialBarrier": (capi.POT_TWOBODY_BARRIER, lambda j: (_get(j, "sets"), [_get(j["functor"], "R0"), _get(j["functor"], "V0")])),
     "potentialThreeBodyUnDis/squareWell": (capi.POT_THREEBODY_UNDIS_SQUAREWELL, lambda j: (_get(j, "sets"), [_get(j["functor"], "R0"), _get(j["functor"], "V0")])),
     "potentialThreeBodyUnDis/potentialBarrier": (capi.POT_THREEBODY_UNDIS_BARRIER, lambda j: (_get(j, "sets"), [_get(j["functor"], "R0"), _get(j["functor"], "V0")])),
+    "potentialThreeBodyDis/squareWell": (capi.POT_THREEBODY_DIS_SQUAREWELL, lambda j: (_get(j, "sets"), [_get(j["functor"], "R0"), _get(j["functor"], "V0")])),
+    "potentialThreeBodyDis/potentialBarrier": (capi.POT_THREEBODY_DIS_BARRIER, lambda j: (_get(j, "sets"), [_get(j["functor"], "R0"), _get(j["functor"], "V0")])),
 }
+# histogram observables over three sets / scalar observables (estimatorsFactory.h:60-95: scalar observables get a
+# realScalarEstimator, which only reads "label"; here they are 1-bin estimators holding sum and count)
+_THREE_SET_HISTOGRAMS = {"trimerCorrelation": capi.EST_TRIMERCORRELATION, "trimerCorrelationDis": capi.EST_TRIMERCORRELATION_DIS}
+_SCALARS = {"trimerhyperRadius": (capi.EST_TRIMERHYPERRADIUS, lambda j: list(_get(j, "sets"))[:3]),
+            "centerOfMassSquared": (capi.EST_CENTEROFMASSSQUARED, lambda j: [_get(j, "set")])}
 
 
 def _dp(a):
@@ -120,7 +128,7 @@ class System:
     def _ck(self, rc):
         if rc:
             msg = self.lib.qmc_last_error(self.ctx).decode()
-            if "Inalid initial" in msg or "set" in msg and "jastrow" in msg:
+            if "Inalid initial" in msg or "set" in msg and "jastrow" in msg or "should be distinguishible" in msg:
                 raise invalidInput(msg)
             raise RuntimeError(msg)
 
@@ -146,6 +154,8 @@ class System:
         sets = [_get(jw, "set")] if kind == "jastrow1b" else list(_get(jw, "sets"))
         if kind == "jastrow3bUnDis":
             sets = sets[:1]
+        if kind == "jastrow3bDis":
+            sets = sets[:3]
         sets = np.asarray(sets, dtype=np.int32)
         hs = float(jw["hardSphereRadius"]) if "hardSphereRadius" in jw else -1.0
         self._ck(self.lib.qmc_add_wavefunction_term(self.ctx, _WAVES[kind], _ip(sets), len(sets), jk, _dp(params), len(params), hs))
@@ -173,6 +183,14 @@ class System:
             sets = np.asarray(_get(jm, "sets")[:1], dtype=np.int32)
             self._ck(self.lib.qmc_add_estimator(self.ctx, capi.EST_TRIMERCORRELATION_UNDIS, _ip(sets), 1, int(jm["bins"]),
                                                 float(jm["minx"]), float(jm["maxx"]), None, 0, C.byref(idx)))
+        elif kind in _THREE_SET_HISTOGRAMS:
+            sets = np.asarray(list(_get(jm, "sets"))[:3], dtype=np.int32)
+            self._ck(self.lib.qmc_add_estimator(self.ctx, _THREE_SET_HISTOGRAMS[kind], _ip(sets), len(sets), int(jm["bins"]),
+                                                float(jm["minx"]), float(jm["maxx"]), None, 0, C.byref(idx)))
+        elif kind in _SCALARS:
+            ek, getsets = _SCALARS[kind]
+            sets = np.asarray(getsets(jm), dtype=np.int32)
+            self._ck(self.lib.qmc_add_estimator(self.ctx, ek, _ip(sets), len(sets), 1, 0.0, 1.0, None, 0, C.byref(idx)))
         elif kind == "structureFactor":
             sets = np.asarray(_get(jm, "sets"), dtype=np.int32)
             extra = np.asarray([jm["maxq"], jm["lBox"], jm["channel"]], dtype=np.float64)
@@ -180,7 +198,7 @@ class System:
                                                 0.0, 0.0, _dp(extra), 3, C.byref(idx)))
         else:
             raise factoryIdNotRecorded(kind)
-        plain = dict(label=jm.get("label", kind), kind=kind, bins=int(jm["bins"]), index=idx.value,
+        plain = dict(label=jm.get("label", kind), kind=kind, bins=int(jm.get("bins", 1)), index=idx.value, scalar=kind in _SCALARS,
                      minx=float(jm.get("minx", 0.0)), maxx=float(jm.get("maxx", 0.0)))
         if "forwardWalkingSteps" in jm:
             # estimatorsFactory.cpp:47-74: one forward-walking estimator "<label>_fw<steps>" per entry INSTEAD of

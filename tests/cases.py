@@ -53,6 +53,48 @@ def mixture():
                              {"kind": "pairCorrelation", "label": "g00", "sets": [0, 0], "bins": 30, "minx": 0.1, "maxx": 2.5}]}
 
 
+def mixture3(hs=None, N=(5, 4, 3), L=4.0):
+    """three DIFFERENT species: jastrow3bDis + potentialThreeBodyDis + trimerCorrelationDis"""
+    w3 = {"kind": "jastrow3bDis", "sets": [0, 1, 2], "jastrow": {"kind": "gaussiangaussian", "r0": 1.5, "u0": -0.2}}
+    if hs is not None:
+        w3["hardSphereRadius"] = hs
+    return {"N": list(N), "lBox": [L] * 3, "method": "dmc", "timeStep": 1e-3, "walkers": 24, "seed": 9,
+            "stepsPerBlock": 10, "nBlocks": 1, "correlationSteps": 0,
+            "wavefunctions": [{"kind": "jastrow2bUnDis", "sets": [0, 0], "jastrow": dict(GG)},
+                              {"kind": "jastrow2bDis", "sets": [1, 2], "jastrow": {"kind": "gaussiangaussian", "r0": 0.9, "u0": 0.3}},
+                              w3],
+            "potentials": [{"kind": "potentialThreeBodyDis", "sets": [0, 1, 2], "functor": {"kind": "squareWell", "R0": 1.8, "V0": 1.0}},
+                           {"kind": "potentialThreeBodyDis", "sets": [0, 1, 2], "functor": {"kind": "potentialBarrier", "R0": 1.2, "V0": 0.7}}],
+            "measurements": [{"kind": "trimerCorrelationDis", "label": "trimerDis", "sets": [0, 1, 2], "bins": 20, "minx": 0.0, "maxx": 2.0},
+                             {"kind": "centerOfMassSquared", "label": "cm2", "set": 1}]}
+
+
+def impurity(N=(6, 5, 1), L=4.0):
+    """two species around ONE impurity (set C holds one particle): trimerCorrelation + trimerhyperRadius"""
+    return {"N": list(N), "lBox": [L] * 3, "method": "dmc", "timeStep": 1e-3, "walkers": 24, "seed": 10,
+            "stepsPerBlock": 10, "nBlocks": 1, "correlationSteps": 0,
+            "wavefunctions": [{"kind": "jastrow2bDis", "sets": [0, 2], "jastrow": dict(GG)},
+                              {"kind": "jastrow2bDis", "sets": [1, 2], "jastrow": {"kind": "gaussiangaussian", "r0": 0.8, "u0": -0.4}},
+                              {"kind": "jastrow3bDis", "sets": [0, 1, 2], "jastrow": {"kind": "poschTeller", "R0": 1.0, "C": 1.0, "alpha": 0.5, "Rm": 1.5, "cut_off": 4.0}}],
+            "potentials": [{"kind": "potentialTwoBody", "sets": [0, 2], "functor": {"kind": "squareWell", "R0": 1.0, "V0": 2.0}}],
+            "measurements": [{"kind": "trimerCorrelation", "label": "trimer", "sets": [0, 1, 2], "bins": 16, "minx": 0.0, "maxx": 2.0},
+                             {"kind": "trimerhyperRadius", "label": "hyper", "sets": [0, 1, 2]},
+                             {"kind": "centerOfMassSquared", "label": "cm2", "set": 0}]}
+
+
+NEW_PATH_EVAL_CASES = ("mixture3", "mixture3_hs", "impurity")     # GPU-tested from tests/test_zz_gpu_new_paths.py
+
+
+def three_set_hist_cases():
+    """observables over three sets and scalar observables, evaluated on given configurations"""
+    return {"mixture3": mixture3(), "impurity": impurity()}
+
+
+def meas_bins(m):
+    """bins of a measurement: scalar observables are 1-bin estimators (sum, count)"""
+    return int(m.get("bins", 1))
+
+
 SPLINE_COEF = [-6.80202700e-05, 3.40101350e-05, -6.80202700e-05, -3.74111485e-04] + [-(0.0101010101 * (i - 1)) ** 2 for i in range(4, 102)]
 
 JASTROWS = {
@@ -99,6 +141,10 @@ def eval_cases():
     N, L = 8, 4.0
     g = np.array([[x, y, z] for x in (0., 2.) for y in (0., 2.) for z in (0., 2.)]).T.reshape(-1)
     out["lattice_ties_N8"] = (pbc(N, L), np.stack([g, g + 4.0, -g]))
+    # distinguishable three-body terms (appended last: the seeded stream of the cases above is unchanged)
+    out["mixture3"] = (mixture3(), rng.uniform(-2.0, 2.0, size=(6, 36)))
+    out["mixture3_hs"] = (mixture3(hs=1.3), rng.uniform(-2.0, 2.0, size=(12, 36)))
+    out["impurity"] = (impurity(), rng.uniform(-2.0, 2.0, size=(6, 36)))
     return out
 
 
@@ -126,7 +172,13 @@ def forward_walking_cases():
     m["measurements"] = [{"kind": "pairCorrelation", "label": "g00", "sets": [0, 0], "bins": 9, "minx": 0.1, "maxx": 1.5},
                          dict({"kind": "pairCorrelation", "label": "g01", "sets": [0, 1], "bins": 10, "minx": 0.0, "maxx": 1.5},
                               recordSteps=5, forwardWalkingSteps=[4, 2])]
-    return {"pbc_pair": p, "three_body_trimer": t, "mixture_g01": m}
+    # scalar observable with a record ring (realScalarStorer / realScalarForwardWalkingEstimator,
+    # correlationEstimator.cpp:5-80) next to a plain three-set histogram; appended last (seeded fixtures)
+    h = impurity(N=(3, 3, 1), L=3.0)
+    h.update(timeStep=2e-2, walkers=20, delta_walkers=3)
+    h["measurements"] = [{"kind": "trimerCorrelation", "label": "trimer", "sets": [0, 1, 2], "bins": 8, "minx": 0.0, "maxx": 1.5},
+                         {"kind": "trimerhyperRadius", "label": "hyper", "sets": [0, 1, 2], "recordSteps": 3, "forwardWalkingSteps": [0, 2]}]
+    return {"pbc_pair": p, "three_body_trimer": t, "mixture_g01": m, "impurity_hyper": h}
 
 
 def fw_measurement(cfg):

@@ -69,6 +69,15 @@ def main():
     pops = np.stack([rng.integers(0, 60, size=8) for _ in range(40)])
     srcs, amts = zip(*[ref.plan(p) for p in pops])
     pieces["plan/pops"], pieces["plan/sources"], pieces["plan/amounts"] = pops, np.stack(srcs), np.stack(amts)
+    # three-set histogram observables and scalar observables (own stream: the fixtures above do not move)
+    rng2 = np.random.default_rng(515151)
+    for name, cfg in cases.three_set_hist_cases().items():
+        R = rng2.uniform(-cfg["lBox"][0] / 2, cfg["lBox"][0] / 2, size=(10, 3 * sum(cfg["N"])))
+        pieces["hist_" + name + "/R"] = R
+        for i, m_ in enumerate(cfg["measurements"]):
+            s, w = ref.histogram(cfg, R, i, cases.meas_bins(m_))
+            pieces["hist_%s/sums%d" % (name, i)] = s
+            pieces["hist_%s/weight%d" % (name, i)] = np.asarray([w])
     np.savez_compressed(os.path.join(HERE, "pieces.npz"), **pieces)
 
     # forward walking: the reference's storer + forward-walking estimator classes over synthetic genealogies
@@ -82,7 +91,7 @@ def main():
         # index in the vector estimatorFactory::create returns: plain estimators before it count one each
         first = sum(len(m_.get("forwardWalkingSteps", [0])) if "forwardWalkingSteps" in m_ else 1 for m_ in cfg["measurements"][:iM])
         for k, steps in enumerate(meas["forwardWalkingSteps"]):
-            sums, w = ref.forward_walking(cfg, pops, ancs, first + k, meas["bins"])
+            sums, w = ref.forward_walking(cfg, pops, ancs, first + k, cases.meas_bins(meas))
             fwd["%s/fw%d/sums" % (name, steps)] = sums
             fwd["%s/fw%d/weight" % (name, steps)] = np.asarray(w)
     np.savez_compressed(os.path.join(HERE, "forward_walking.npz"), **fwd)

@@ -26,7 +26,7 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-@pytest.mark.parametrize("name", sorted(cases.eval_cases()))
+@pytest.mark.parametrize("name", sorted(n for n in cases.eval_cases() if n not in cases.NEW_PATH_EVAL_CASES))
 def test_eval_vs_golden_and_oracle(port, name):
     cfg, R = cases.eval_cases()[name]
     s = System.from_input(cfg)

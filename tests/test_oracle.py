@@ -74,6 +74,33 @@ def test_histograms(port, name):
         assert s.sum() > 0
 
 
+@pytest.mark.parametrize("name", sorted(cases.three_set_hist_cases()))
+def test_three_set_and_scalar_observables(port, name):
+    """trimerCorrelation / trimerCorrelationDis (histograms) and trimerhyperRadius / centerOfMassSquared
+    (scalars: sum and count of a realScalarEstimator) against the fixtures produced by the reference"""
+    cfg = cases.three_set_hist_cases()[name]
+    R = PIECES["hist_" + name + "/R"]
+    for i, m in enumerate(cfg["measurements"]):
+        s, w = port.histogram(cfg, R, i, cases.meas_bins(m))
+        assert w == PIECES["hist_%s/weight%d" % (name, i)][0] == len(R)
+        assert rel(s, PIECES["hist_%s/sums%d" % (name, i)]) < TOL, m["kind"]
+        assert s.sum() > 0
+
+
+def test_three_set_observables_match_reference_itself(port, ref):
+    for name, cfg in cases.three_set_hist_cases().items():
+        R = np.random.default_rng(77).uniform(-2, 2, size=(5, 3 * sum(cfg["N"])))
+        for i, m in enumerate(cfg["measurements"]):
+            a, wa = ref.histogram(cfg, R, i, cases.meas_bins(m))
+            b, wb = port.histogram(cfg, R, i, cases.meas_bins(m))
+            assert wa == wb and rel(b, a) < TOL, (name, m["kind"])
+
+
+def test_distinguishable_constraint_case_has_invalid_walkers():
+    v = EVAL["mixture3_hs/valid"]
+    assert 0 < v.sum() < len(v)
+
+
 @pytest.mark.parametrize("tag", ["lower", "upper", "window"])
 def test_branching_matches_reference(port, tag):
     """tst/dmc-test.cpp:15-153 (branching_lower/upper): population == sum nDescendants, each
@@ -212,7 +239,7 @@ def test_forward_walking_matches_golden(port, name):
     iM, meas = cases.fw_measurement(cfg)
     pops, ancs = _fw_genealogy(name)
     for steps in meas["forwardWalkingSteps"]:
-        sums, w = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, meas["bins"])
+        sums, w = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, cases.meas_bins(meas))
         assert w == float(FWD["%s/fw%d/weight" % (name, steps)]) and w > 0
         np.testing.assert_allclose(sums, FWD["%s/fw%d/sums" % (name, steps)], rtol=1e-13, atol=0)
 
@@ -222,8 +249,8 @@ def test_forward_walking_matches_reference_itself(port, ref):
     iM, meas = cases.fw_measurement(cfg)
     pops, ancs = cases.synthetic_genealogy(cfg, 7, 5, 99)
     for k, steps in enumerate(meas["forwardWalkingSteps"]):
-        a, wa = ref.forward_walking(cfg, pops, ancs, k, meas["bins"])
-        b, wb = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, meas["bins"])
+        a, wa = ref.forward_walking(cfg, pops, ancs, k, cases.meas_bins(meas))
+        b, wb = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, cases.meas_bins(meas))
         assert wa == wb
         np.testing.assert_allclose(b, a, rtol=1e-13, atol=0)
 

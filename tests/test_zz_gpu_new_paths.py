@@ -60,7 +60,7 @@ def test_forward_walking_vs_oracle_on_the_traced_genealogy(port, name, sample_ev
     for steps in meas["forwardWalkingSteps"]:
         e = s.estimators[labels.index("%s_fw%d" % (meas["label"], steps))]     # estimatorsFactory.cpp:58
         got, w = s.estimator(e["index"])
-        exp, we = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, meas["bins"])
+        exp, we = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], steps, cases.meas_bins(meas))
         assert w == we and w > 0
         assert rel(got, exp) < RTOL, steps
     assert meas["label"] not in labels                 # the plain estimator is replaced, not added (estimatorsFactory.cpp:47)
@@ -81,7 +81,7 @@ def test_forward_walking_ring_restarts_with_a_new_population(port):
     assert s.info("fw_events") == 6
     e = s.estimators[0]
     got, w = s.estimator(e["index"])
-    exp, we = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], e["forwardWalkingSteps"], meas["bins"])
+    exp, we = port.forward_walking(cfg, pops, ancs, iM, meas["recordSteps"], e["forwardWalkingSteps"], cases.meas_bins(meas))
     assert w == we and rel(got, exp) < RTOL
     s.close()
 
@@ -125,3 +125,126 @@ def test_forward_walking_measurement_files(tmp_path):
     bad["measurements"][0].update(recordSteps=4, forwardWalkingSteps=[1])
     p = hd.run(bad, str(tmp_path))
     assert p.returncode != 0 and "Forward walking estimator for vector" in p.stderr
+
+
+# ---- distinguishable three-body terms, three-set observables, scalar observables ---------
+import test_gpu_parity as gp  # noqa: E402
+
+PIECES = gp.PIECES
+
+
+@pytest.mark.parametrize("name", cases.NEW_PATH_EVAL_CASES)
+def test_distinguishable_three_body_eval_vs_golden_and_oracle(port, name):
+    """jastrow3bDis + potentialThreeBodyDis + hardSphereConstraintThreeBodyDis: per-configuration parity (1)
+    against the reference's golden vectors and the oracle"""
+    gp.test_eval_vs_golden_and_oracle(port, name)
+
+
+@pytest.mark.parametrize("wpw", ["1", "2", "4", "8"])
+def test_distinguishable_three_body_independent_of_work_decomposition(port, wpw, monkeypatch):
+    monkeypatch.setenv("QMC4_WPW", wpw)
+    cfg, R = cases.eval_cases()["mixture3"]
+    s = System.from_input(cfg)
+    assert s.info("warps_per_walker") == int(wpw)
+    o = s.eval(R)
+    s.close()
+    r = port.eval(cfg, R)
+    for k in ("logpsi", "grad", "lap", "V", "E"):
+        assert rel(o[k], r[k]) < RTOL, k
+
+
+@pytest.mark.parametrize("name", ["mixture3", "impurity"])
+def test_distinguishable_three_body_traced_step(port, name):
+    gp.test_traced_step_vs_oracle_update(port, name)
+
+
+def test_distinguishable_constraint_rejects_and_invalid_start_throws(port):
+    cfg, R = cases.eval_cases()["mixture3_hs"]
+    valid = gp.EVAL["mixture3_hs/valid"].astype(bool)
+    cfg = dict(cfg, walkers=int(valid.sum()), timeStep=0.05)
+    s = System.from_input(cfg)
+    with pytest.raises(Exception, match="Inalid initial"):
+        s.upload(R)                              # dmcDriver.cpp:166-170
+    s.close()
+    s = System.from_input(cfg)
+    s.upload(R[valid])
+    tr = s.step_traced()
+    ep = port.eval(cfg, tr["Rprop"])
+    np.testing.assert_array_equal(tr["valid"], ep["valid"])
+    assert not (tr["accepted"][tr["valid"] == 0]).any()
+    s.close()
+
+
+@pytest.mark.parametrize("name", sorted(cases.three_set_hist_cases()))
+def test_three_set_and_scalar_observables_on_given_configurations(port, name):
+    """trimerCorrelation, trimerCorrelationDis (histograms), trimerhyperRadius, centerOfMassSquared (scalars:
+    sum of the observable and number of walkers) against the fixtures produced by the reference"""
+    cfg = cases.three_set_hist_cases()[name]
+    R = PIECES["hist_" + name + "/R"]
+    s = System.from_input(cfg)
+    s.accumulate_configs(R)
+    for i, m in enumerate(cfg["measurements"]):
+        sums, w = s.estimator(s.estimators[i]["index"])
+        assert w == PIECES["hist_%s/weight%d" % (name, i)][0]
+        assert rel(sums, PIECES["hist_%s/sums%d" % (name, i)]) < RTOL, m["kind"]
+    s.clear_estimators()
+    sums, w = s.estimator(s.estimators[0]["index"])
+    assert w == 0 and not sums.any()
+    s.close()
+
+
+@pytest.mark.parametrize("name", sorted(cases.three_set_hist_cases()))
+def test_three_set_and_scalar_observables_in_the_step_use_branching_weights(port, name):
+    """accumulated inside the step == oracle over the post-branching population (dmcDriver.cpp:257-264)"""
+    cfg = dict(cases.three_set_hist_cases()[name], walkers=48, timeStep=0.05)
+    R = np.random.default_rng(31).uniform(-2, 2, size=(48, 3 * sum(cfg["N"])))
+    s = System.from_input(cfg)
+    s.upload(R)
+    tr = s.step_traced(accumulate=True)
+    assert (tr["n_desc"] != 1).any()
+    Rn = s.download()
+    for i, m in enumerate(cfg["measurements"]):
+        sums, w = s.estimator(s.estimators[i]["index"])
+        ref_s, ref_w = port.histogram(cfg, Rn, i, cases.meas_bins(m))
+        assert w == ref_w == len(Rn)
+        assert rel(sums, ref_s) < 1e-9, m["kind"]
+    s.close()
+
+
+def test_three_set_observable_errors():
+    cfg = cases.impurity(N=(4, 3, 2))                 # set C must hold one particle (assert, trimerCorrelation.cpp:11)
+    with pytest.raises(Exception, match="one particle"):
+        System.from_input(cfg)
+    cfg = cases.mixture3()
+    cfg["wavefunctions"][2]["sets"] = [0, 1, 1]       # jastrowWavefunctionThreeBody.h:173-176
+    with pytest.raises(Exception, match="should be distinguishible"):
+        System.from_input(cfg)
+
+
+def test_host_driver_three_set_and_scalar_measurement_files(tmp_path):
+    """dmc_b200 with the reference's input for an impurity system: <label>.dat of a scalar observable is the
+    label followed by one average per block in %.12e (realScalarEstimator::write, estimators.cpp:89-98);
+    trimerCorrelation is a histogram file; a scalar forward-walking estimator writes <label>_fw<k>.dat"""
+    cfg = dict(cases.impurity(), walkers=16, delta_walkers=2, nBlocks=3, stepsPerBlock=4)
+    cfg["measurements"].append({"kind": "trimerhyperRadius", "label": "hfw", "sets": [0, 1, 2], "recordSteps": 3, "forwardWalkingSteps": [1]})
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    for label in ("hyper", "cm2"):
+        lines = open(tmp_path / (label + ".dat")).read().split("\n")
+        vals = [x for x in lines[1:] if x.strip()]
+        assert lines[0] == label and len(vals) == 3
+        assert all(len(v.split("e")[0].split(".")[1]) == 12 and float(v) > 0 for v in vals)
+    blocks = open(tmp_path / "trimer.dat").read().strip().split("\n\n")
+    assert blocks[0].split("\n")[0] == "x trimer" and len(blocks) == 3
+    fw = open(tmp_path / "hfw_fw1.dat").read().split("\n")
+    assert fw[0] == "hfw_fw1" and len([x for x in fw[1:] if x.strip()]) == 3 - 0       # 4 sampling events per block >= recordSteps
+    assert not os.path.exists(tmp_path / "hfw.dat")
+    # a three-species input with jastrow3bDis + potentialThreeBodyDis runs end to end
+    cfg = dict(cases.mixture3(), walkers=12, delta_walkers=2, nBlocks=2, stepsPerBlock=3)
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    assert os.path.exists(tmp_path / "trimerDis.dat")
+    bad = cases.mixture3()
+    bad["potentials"][0]["sets"] = [0, 0, 2]
+    p = hd.run(bad, str(tmp_path))
+    assert p.returncode != 0 and "should be distinguishible" in p.stderr
