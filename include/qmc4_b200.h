@@ -163,6 +163,14 @@ int  qmc_add_forward_walking(qmc_ctx *ctx, int est_index, int record_steps,
 int  qmc_set_dmc(qmc_ctx *ctx, double timeStep, int64_t targetWalkers, int64_t deltaWalkers,
                  uint64_t seed, int branching_on, int64_t capacity);
 
+/* Many-chain VMC in place of qmc_set_dmc: every walker is an independent Metropolis chain of vmcDriver
+ * (vmcDriver.cpp:12-84): gaussianMover x' = x + xi*sqrt(sigma) with sigma = the input's "timeStep"
+ * (vmcMoves.cpp:11-35, main.cpp:314), acceptance min(1, |psi(x')/psi(x)|^2) (vmcDriver.cpp:68,
+ * metropolis.cpp:5-29), constraint violation = rejection (:73-77), no branching; the energy estimator
+ * is the local energy of the current configuration (energy.cpp:28-35).  The reference runs ONE chain
+ * per MPI rank; nChains > 1 is the GPU extension (statistically equivalent: chains are independent). */
+int  qmc_set_vmc(qmc_ctx *ctx, double sigma, int64_t nChains, uint64_t seed, int64_t capacity);
+
 /* Parity entry (1): evaluate nW configurations given in HOST memory; any output may be NULL.
  * = initializer::initialize + updateForceGradientEnergy (initializer.cpp:75-82, walkers.cpp:46-61). */
 int  qmc_eval(qmc_ctx *ctx, const double *R, int64_t nW,

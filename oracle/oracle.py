@@ -293,6 +293,19 @@ class Port(_Base):
                                            _dp(out["logpsi"]), _dp(out["E"]), _ip(out["accepted"])))
         return out
 
+    def vmc_step(self, cfg, sigma, Rold, xi_layout, u_m):
+        """vmcDriver::step for every chain given the random numbers it consumes."""
+        m = self._model(cfg)
+        d = _dofs(cfg)
+        Rold = np.ascontiguousarray(Rold, dtype=np.float64).reshape(-1, d)
+        nW = Rold.shape[0]
+        xi = self.draw_order(cfg, xi_layout)
+        u_m = np.ascontiguousarray(u_m, dtype=np.float64)
+        out = dict(R=np.zeros((nW, d)), logpsi=np.zeros(nW), E=np.zeros(nW), accepted=np.zeros(nW, dtype=np.int32))
+        self._ck(self.lib.orc_vmc_step_model(C.byref(m), C.c_double(sigma), nW, _dp(Rold), _dp(xi), _dp(u_m), _dp(out["R"]),
+                                             _dp(out["logpsi"]), _dp(out["E"]), _ip(out["accepted"])))
+        return out
+
     def histogram(self, cfg, R, iMeas, bins):
         m = self._model(cfg)
         d = _dofs(cfg)

@@ -794,6 +794,50 @@ int orc_update_model(const orc_model *m, double timeStep, int nW, const double *
   return rc;
 }
 
+/* One vmcDriver::step (dmc/vmcDriver.cpp:55-84) per chain given the random numbers it consumes: gaussianMover
+ * x' = x + xi*sqrt(sigma) in draw order (vmcMoves.cpp:22-33), update (:38-52: constraints, log psi), acceptLog on
+ * 2*(log psi' - log psi) (:68), invalid = rejected (:73-77), reject restores the old walker (:79-82).  E_out is the
+ * `energy` observable the driver accumulates on the current walker (energy.cpp:28-35). */
+int orc_vmc_step_model(const orc_model *m, double sigma, int nW, const double *Rold, const double *xi, const double *u_m,
+                       double *Rout, double *logpsi_out, double *E_out, int *accepted)
+{
+  int dofs = 0;
+  for (int s = 0; s < m->nSpecies; s++) dofs += 3 * m->N[s];
+  double *Fo = malloc(sizeof(double) * dofs), *Fn = malloc(sizeof(double) * dofs), *Rn = malloc(sizeof(double) * dofs);
+  int rc = 0;
+  for (int w = 0; w < nW && !rc; w++)
+    {
+      const double *Ro = Rold + (size_t)w * dofs, *x = xi + (size_t)w * dofs;
+      eval_out eo, en;
+      rc = evaluate(m, Ro, Fo, &eo);
+      if (rc) break;
+      int off = 0, kk = 0;
+      for (int s = 0; s < m->nSpecies; s++)
+        {
+          int N = m->N[s];
+          for (int i = 0; i < N; i++)
+            for (int d = 0; d < 3; d++) Rn[off + d * N + i] = Ro[off + d * N + i] + x[kk++] * sqrt(sigma);
+          off += 3 * N;
+        }
+      rc = evaluate(m, Rn, Fn, &en);
+      if (rc) break;
+      int acc = 0;
+      if (en.valid)
+        {
+          double ratioLog = 2 * (en.logpsi - eo.logpsi);
+          acc = (ratioLog > 0.) ? 1 : (ratioLog > log(u_m[w]));
+        }
+      accepted[w] = acc;
+      for (int k = 0; k < dofs; k++) Rout[(size_t)w * dofs + k] = acc ? Rn[k] : Ro[k];
+      logpsi_out[w] = acc ? en.logpsi : eo.logpsi;
+      E_out[w] = acc ? en.E : eo.E;
+    }
+  free(Fo);
+  free(Fn);
+  free(Rn);
+  return rc;
+}
+
 /* ---- estimators --------------------------------------------------------------------------------- */
 static void hist_accumulate(double *sums, double minx, double dxinv, double a, double x)
 { /* histogramAccumulator::accumulate (accumulators.h:117) */

@@ -64,6 +64,10 @@ int orc_plan(const int *populations, int nRanks, int *sources, int *amounts);
 int orc_update_model(const orc_model *m, double timeStep, int nW, const double *Rold, const double *xi_draw_order,
                      const double *u_m, double *Rout, double *Fout, double *logpsi_out, double *E_out, int *accepted);
 
+/* one vmcDriver::step (dmc/vmcDriver.cpp:55-84) per chain given xi (draw order) and the Metropolis uniform */
+int orc_vmc_step_model(const orc_model *m, double sigma, int nW, const double *Rold, const double *xi_draw_order,
+                       const double *u_m, double *Rout, double *logpsi_out, double *E_out, int *accepted);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1160,6 +1160,22 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
   return 0;
 }
 
+int qmc_set_vmc(qmc_ctx *c, double sigma, int64_t nChains, uint64_t seed, int64_t capacity)
+{
+  if (!c) return 1;
+  if (!(sigma > 0) || nChains < 1) return fail(c, "qmc_set_vmc: sigma > 0 and at least one chain");
+  if (!c->fw_est.empty()) return fail(c, "forward walking needs branching genealogies: use method dmc");
+  c->pipeline = 1;                      /* the Green-ratio switch lives in propagate_kernel */
+  if (capacity <= 0) capacity = nChains / std::max(1, c->nranks) + 64;
+  if (qmc_set_dmc(c, sigma, nChains, 0, seed, 0, capacity)) return 1;
+  DmcParams &D = c->dmc;
+  D.tau = 0.0;                          /* no drift:  x' = x + xi*sqrt(sigma)  (vmcMoves.cpp:31) */
+  D.sqrt_tau = std::sqrt(sigma);
+  D.log_up = D.log_down = 0.0;
+  D.vmc = 1;
+  return 0;
+}
+
 static int eval_common(qmc_ctx *c, const double *dR, int64_t nW, double *dlogpsi, double *dgrad, double *dlap,
                        double *dV, double *dE, int *dvalid, bool hist, int flag_invalid)
 {

@@ -170,7 +170,7 @@ propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
       const u32x4 rd = philox4x32_10({(uint32_t)j, 0xffffffffu, step_lo, step_hi}, dmc.seed_lo, dmc.seed_hi);
       const double u_m = u01_53(rd.x, rd.y);
       const double u_b = u01_53(rd.z, rd.w);
-      const double A = 2.0 * (r.logpsi - lp_old) + qs;
+      const double A = 2.0 * (r.logpsi - lp_old) + (dmc.vmc ? 0.0 : qs);     /* vmc: vmcDriver.cpp:68 */
       const bool accepted = r.valid && (A > 0.0 || A > log(u_m));
       const double Efin = accepted ? Enew : Eold;
       int n = 1;

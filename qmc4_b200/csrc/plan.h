@@ -99,7 +99,8 @@ struct DmcParams {
   uint32_t seed_lo, seed_hi;
   int branching_on;
   int rank, nranks;
-  int pad;
+  int vmc;                   // 1: many-chain VMC (vmcDriver.cpp:55-84): Gaussian move without drift (tau = 0, sqrt_tau = sqrt(sigma),
+                             //    vmcMoves.cpp:11-35), acceptance |psi'|^2/|psi|^2 only (no Green-function ratio), no branching
 };
 
 } // namespace qmc

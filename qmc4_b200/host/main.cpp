@@ -1,5 +1,5 @@
 // dmc_b200 — the host driver: `dmc_b200 < input.json` or `dmc_b200 input.json [--gpus N]`, the reference's
-// CLI and input schema (dmc/main.cpp:105-428) for method "dmc" / "svmc", running on B200 through the C ABI.
+// CLI and input schema (dmc/main.cpp:105-428) for method "dmc" / "svmc" / "vmc", running on B200 through the C ABI.
 // Multi-GPU: one host thread per GPU inside this process stands for one MPI rank of the reference
 // (seed, population split and per-rank configuration files follow main.cpp:383,391 and walkers.cpp:225).
 #include "qmc4host.h"
@@ -64,12 +64,19 @@ static void runRank(const json_t &j, int rank, int nranks, const void *uid, int 
             std::cout << ansiColor("yellow") << "WARNING: Failed to load configurations from directory. Falling back to randomly generated configurations."
                       << ansiColor("default") << std::endl;
         }
-      if (method != "dmc" && method != "svmc")
-        throw missingImplementation("method '" + method + "': only dmc and svmc run on the GPU path (single-walker vmc stays on the CPU code)");
+      if (method != "dmc" && method != "svmc" && method != "vmc")
+        throw missingImplementation("method '" + method + "': dmc, svmc and vmc run on the GPU path");
+      const bool vmc = method == "vmc";
+      if (vmc && j.contains("measurements"))
+        for (const json_t &m : j["measurements"].elements())
+          if (m["kind"].get<std::string>() == "superfluidFraction")
+            throw invalidInput("Cannot have vmc and superfluid fraction measurements");        /* main.cpp:279-282 */
       /* every rank registers the estimators (the device accumulates everywhere and the block reduction is a
          collective); only rank 0 writes the files (estimators.cpp:40,58) */
       std::vector<estimatorBase *> ests = f.createEstimators(j.contains("measurements") ? j["measurements"] : json_t::parse("[]"));
-      const size_t nW = j["walkers"].get<int>();
+      /* vmc: the reference runs ONE chain per MPI rank (vmcDriver.cpp:21-36) and does not read "walkers"; on the GPU the
+         optional "walkers" key asks for that many independent chains (extension; default one chain per GPU) */
+      const size_t nW = vmc ? (size_t)(j.contains("walkers") ? j["walkers"].get<int>() : nranks) : (size_t)j["walkers"].get<int>();
       size_t delta_walkers = size_t(nW * 0.1);
       if (j.contains("delta_walkers")) delta_walkers = j["delta_walkers"].get<int>();
       dmcDriver dmcO(&psi, &pot, timeStep, nW, delta_walkers);
@@ -90,6 +97,7 @@ static void runRank(const json_t &j, int rank, int nranks, const void *uid, int 
             throw invalidInput("Initial configuration does not math the numper of particles defined in the input file");
       dmcO.getRandomGenerator().seed((unsigned long long)seed + rank);
       if (method == "svmc") dmcO.disableBranching();
+      if (vmc) dmcO.enableVmc();
       for (auto *e : ests) dmcO.getEstimators().push_back(e);
       dmcO.run(dmcStates, nBlocks);
       for (auto *w : waves) delete w;

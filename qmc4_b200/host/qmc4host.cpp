@@ -369,7 +369,8 @@ void dmcDriver::run(const std::vector<states_t> &states, size_t nBlocks)
   if (master) energyEst.reset(new realScalarEstimator("energy"));        /* registered first (dmcDriver.cpp:245) */
   for (auto *e : estimators) e->registerOn(ctx);
   if (nranks > 1) check(qmc_comm_init(ctx, uid, rank, nranks));
-  check(qmc_set_dmc(ctx, timeStep, (int64_t)nWalkers, (int64_t)deltaWalkers, rng.value, performBranching ? 1 : 0, 0));
+  if (vmcMode) check(qmc_set_vmc(ctx, timeStep, (int64_t)nWalkers, rng.value, 0));
+  else check(qmc_set_dmc(ctx, timeStep, (int64_t)nWalkers, (int64_t)deltaWalkers, rng.value, performBranching ? 1 : 0, 0));
   dofs = 0;
   speciesN = N;
   for (int n : N) dofs += 3 * n;
@@ -420,13 +421,16 @@ void dmcDriver::out(size_t iBlock)
       energyEst->collect(ctx, r);
       std::cout << ansiColor("green") << "Block: " << ansiColor("default") << iBlock << std::endl;
       std::cout << "Acc. Ratio: " << r.n_accepted / r.n_moves << std::endl;
-      std::cout << "Step: " << (iBlock + 1) * _stepsPerBlock << std::endl;
+      if (!vmcMode) std::cout << "Step: " << (iBlock + 1) * _stepsPerBlock << std::endl;      /* vmcDriver::out (vmcDriver.cpp:96-121) has no Step line */
       std::cout << ansiColor("cyan") << "Energy: " << ansiColor("default");
       std::cout << std::scientific;
       energyEst->write(std::cout);
       std::cout << std::endl << std::defaultfloat;
-      std::cout << ansiColor("cyan") << "Curr. Walkers: " << ansiColor("default");
-      std::cout << (long)r.population << std::endl;
+      if (!vmcMode)
+        {
+          std::cout << ansiColor("cyan") << "Curr. Walkers: " << ansiColor("default");
+          std::cout << (long)r.population << std::endl;
+        }
       energyEst->dump();
       for (auto *e : estimators) e->dump();
     }

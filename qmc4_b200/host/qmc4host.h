@@ -559,6 +559,9 @@ class dmcDriver {
   std::vector<estimatorBase *> &getEstimators() { return estimators; }
   seedHolder &getRandomGenerator() { return rng; }
   void disableBranching() { performBranching = false; }
+  // method "vmc" (vmcDriver.cpp): nWalkers independent Metropolis chains with the Gaussian mover of vmcMoves.cpp:11-35
+  // (sigma = timeStep) and the |psi|^2 acceptance; the block report is vmcDriver::out's (no Step / Curr. Walkers lines)
+  void enableVmc() { vmcMode = true; performBranching = false; }
   void setDevice(int d) { device = d; }
   void setComm(const void *uniqueId, int rank_, int nranks_) { uid = uniqueId; rank = rank_; nranks = nranks_; }
   void setOutput(bool on) { master = on; }
@@ -577,7 +580,7 @@ class dmcDriver {
   std::vector<estimatorBase *> estimators;
   std::unique_ptr<realScalarEstimator> energyEst;
   seedHolder rng;
-  bool performBranching = true, master = true;
+  bool performBranching = true, master = true, vmcMode = false;
   int device = 0, rank = 0, nranks = 1;
   const void *uid = nullptr;
   qmc_ctx *ctx = nullptr;

@@ -233,6 +233,9 @@ class System:
         self._ck(self.lib.qmc_set_dmc(self.ctx, float(timeStep), int(walkers), int(delta_walkers), int(seed),
                                       1 if branching else 0, int(capacity)))
 
+    def set_vmc(self, sigma, chains=1, seed=0, capacity=0):
+        self._ck(self.lib.qmc_set_vmc(self.ctx, float(sigma), int(chains), int(seed), int(capacity)))
+
     @classmethod
     def from_input(cls, j, device=0, comm=None, capacity=0):
         """j: the reference's input document (dict).  comm: None or (unique_id, rank, nranks)."""
@@ -252,6 +255,10 @@ class System:
             s.comm_init(*comm)
         method = j.get("method", "dmc")
         walkers = int(j.get("walkers", 1))
+        if method == "vmc":          # vmcDriver(&psi, timeStep) (main.cpp:314): "walkers" independent chains on the GPU
+            s.set_vmc(j.get("timeStep", 1e-3), walkers, seed=int(j.get("seed", 0)), capacity=capacity)
+            s.input = j
+            return s
         s.set_dmc(j.get("timeStep", 1e-3), walkers, j.get("delta_walkers"), seed=int(j.get("seed", 0)),
                   branching=(method != "svmc"), capacity=capacity)
         s.input = j

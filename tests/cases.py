@@ -157,6 +157,16 @@ def dmc_cases():
     return {"trap_N10": t, "pbc_N16": p}
 
 
+def vmc_case():
+    """method "vmc" (vmcDriver.cpp): the trap of config 1 sampled from |psi|^2; the reference runs one chain"""
+    t = trap(10)
+    t.update(method="vmc", timeStep=0.1, stepsPerBlock=2000, nBlocks=120, correlationSteps=4, seed=31,
+             initialConditionGenerator={"lBox": [2.0, 2.0, 2.0]})
+    t.pop("walkers")
+    t["measurements"] = [{"kind": "centerOfMassSquared", "label": "cm2", "set": 0}]
+    return t
+
+
 def forward_walking_cases():
     """Small systems with a stored histogram estimator ("recordSteps") and forward-walking estimators
     ("forwardWalkingSteps": [..], estimatorsFactory.cpp:47-74).  name -> cfg."""

@@ -116,6 +116,16 @@ def main():
                 res[name] = entry
         with open(os.path.join(HERE, "dmc_reference_runs.json"), "w") as f:
             json.dump(res, f)
+    if "--vmc" in sys.argv or "--dmc" in sys.argv:
+        cfg = cases.vmc_case()
+        with tempfile.TemporaryDirectory() as tmp:
+            with open(os.path.join(tmp, "input.json"), "w") as f:
+                json.dump(cfg, f)
+            subprocess.check_call([REF_BIN, "input.json"], cwd=tmp, stdout=subprocess.DEVNULL)
+            entry = {"input": cfg, "energy_per_block": np.loadtxt(os.path.join(tmp, "energy.dat"), skiprows=1).tolist(),
+                     "cm2_per_block": np.loadtxt(os.path.join(tmp, "cm2.dat"), skiprows=1).tolist()}
+        with open(os.path.join(HERE, "vmc_reference_run.json"), "w") as f:
+            json.dump(entry, f)
     print("golden fixtures written to", HERE)
 
 

@@ -248,3 +248,82 @@ def test_host_driver_three_set_and_scalar_measurement_files(tmp_path):
     bad["potentials"][0]["sets"] = [0, 0, 2]
     p = hd.run(bad, str(tmp_path))
     assert p.returncode != 0 and "should be distinguishible" in p.stderr
+
+
+# ---- many-chain VMC (method "vmc": vmcDriver.cpp) -----------------------------------------
+@pytest.mark.parametrize("name,sigma", [("trap_N10", 0.3), ("mixture", 0.02), ("pbc_gg_barrier_N33", 0.05), ("mixture3_hs", 0.05)])
+def test_vmc_traced_step_vs_oracle(port, name, sigma):
+    """one vmcDriver::step per chain: Gaussian move without drift, acceptance on 2*(log psi' - log psi) only,
+    rejected / invalid proposals keep the old configuration, no branching — against the oracle's restatement
+    given the random numbers the kernel drew"""
+    cfg, R = cases.eval_cases()[name]
+    valid = port.eval(cfg, R)["valid"].astype(bool)
+    R = R[valid]
+    cfg = dict(cfg, method="vmc", walkers=len(R), timeStep=sigma)
+    s = System.from_input(cfg)
+    s.upload(R)
+    tr = s.step_traced(accumulate=True)
+    assert rel(tr["Rprop"], R + tr["xi"] * np.sqrt(sigma)) < 1e-14            # vmcMoves.cpp:31
+    up = port.vmc_step(cfg, sigma, R, tr["xi"], tr["u_metropolis"])
+    np.testing.assert_array_equal(up["accepted"], tr["accepted"])
+    assert (tr["n_desc"] == 1).all() and tr["n_after"] == len(R)
+    Rn, En = s.download(with_energy=True)
+    assert rel(Rn, up["R"]) < 1e-13 and rel(En, up["E"]) < RTOL
+    b = s.block_results()
+    assert b["n_moves"] == len(R) and b["n_accepted"] == up["accepted"].sum() and b["energy_count"] == len(R)
+    assert abs(b["energy_sum"] - up["E"].sum()) < 1e-9 * np.abs(up["E"]).sum()
+    s.close()
+
+
+def test_vmc_rejections_happen_and_errors():
+    cfg, R = cases.eval_cases()["pbc_gg_barrier_N33"]
+    cfg = dict(cfg, method="vmc", walkers=len(R), timeStep=0.5)
+    s = System.from_input(cfg)
+    s.upload(R)
+    s.step(20, 1)
+    b = s.block_results()
+    assert 0 < b["n_accepted"] < b["n_moves"] == 20 * len(R) and b["population"] == len(R)
+    s.close()
+    fw = cases.forward_walking_cases()["pbc_pair"]
+    with pytest.raises(Exception, match="forward walking needs branching"):
+        System.from_input(dict(fw, method="vmc"))
+
+
+def test_host_driver_vmc_block_report_and_files(tmp_path):
+    """method "vmc": vmcDriver::out's block report (Block / Acc. Ratio / Energy, no Step or Curr. Walkers lines,
+    vmcDriver.cpp:96-121), energy.dat, scalar measurement file, checkpoint of the chains"""
+    import re
+    cfg = dict(cases.vmc_case(), walkers=8, stepsPerBlock=10, nBlocks=3, correlationSteps=1)
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    out = re.sub(r"\x1b\[[0-9;]*m", "", p.stdout)
+    assert out.count("Block: ") == 3 and out.count("Acc. Ratio: ") == 3 and out.count("Energy: ") == 3
+    assert "Curr. Walkers" not in out and "Step: " not in out
+    e = np.loadtxt(tmp_path / "energy.dat", skiprows=1)
+    c = np.loadtxt(tmp_path / "cm2.dat", skiprows=1)
+    assert len(e) == 3 and len(c) == 3 and np.isfinite(e).all() and (c > 0).all()
+    import json
+    ck = json.load(open(tmp_path / "configurations" / "walkers-Rank0.json"))
+    assert len(ck["configurations"]) == 8
+    # without "walkers": one chain per GPU, as the reference runs it
+    cfg.pop("walkers")
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    assert len(json.load(open(tmp_path / "configurations" / "walkers-Rank0.json"))["configurations"]) == 1
+
+
+@pytest.mark.skipif(hd.BIN.endswith("_emu"), reason="statistics need ~1e7 chain steps: hardware only")
+def test_vmc_statistical_parity_with_reference_run(tmp_path):
+    """parity (2) for the VMC leg of BASELINE config 1: variational energy and <cm2> of 512 GPU chains against the
+    reference's own single-chain run (tests/golden/vmc_reference_run.json, generated by make_golden.py --vmc)"""
+    import json
+    ref = json.load(open(os.path.join(hd.GOLD, "vmc_reference_run.json")))
+    cfg = dict(ref["input"], walkers=512, stepsPerBlock=100, nBlocks=60, seed=5)
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    for key, fname in (("energy_per_block", "energy.dat"), ("cm2_per_block", "cm2.dat")):
+        a = np.loadtxt(tmp_path / fname, skiprows=1)[10:]
+        b = np.asarray(ref[key])[20:]
+        sa, sb = hd._blocked_error(a), hd._blocked_error(b)
+        z = abs(a.mean() - b.mean()) / np.hypot(sa, sb)
+        assert z < 3.0, (key, a.mean(), sa, b.mean(), sb)
