@@ -171,6 +171,12 @@ int  qmc_set_dmc(qmc_ctx *ctx, double timeStep, int64_t targetWalkers, int64_t d
  * per MPI rank; nChains > 1 is the GPU extension (statistically equivalent: chains are independent). */
 int  qmc_set_vmc(qmc_ctx *ctx, double sigma, int64_t nChains, uint64_t seed, int64_t capacity);
 
+/* wavefunction::print() -> jastrow<T>::print(minx, maxx, n) (wavefunction.h:64, jastrow.h:42-63; main.cpp:220-227
+ * writes it to wave<i>.dat): u, u', u'' of the radial functor of wavefunction term `wf_index` (order of the
+ * qmc_add_wavefunction_term calls) evaluated ON THE DEVICE at the n bin centres x_i = minx + (i+0.5)(maxx-minx)/n.
+ * out (host): n rows {x, u, u', u''}. */
+int  qmc_tabulate_wavefunction(qmc_ctx *ctx, int wf_index, double minx, double maxx, int64_t n, double *out);
+
 /* Parity entry (1): evaluate nW configurations given in HOST memory; any output may be NULL.
  * = initializer::initialize + updateForceGradientEnergy (initializer.cpp:75-82, walkers.cpp:46-61). */
 int  qmc_eval(qmc_ctx *ctx, const double *R, int64_t nW,

@@ -293,6 +293,15 @@ class Port(_Base):
                                            _dp(out["logpsi"]), _dp(out["E"]), _ip(out["accepted"])))
         return out
 
+    def tabulate(self, jastrow, minx, maxx, n):
+        """jastrow<T>::print for the radial functor given as the input's "jastrow" object"""
+        jk, keys = _J[jastrow["kind"]]
+        params = [jastrow[k] for k in keys] + (list(jastrow["coefficients"]) if jastrow["kind"] == "bSpline" else [])
+        p = np.asarray(params, dtype=np.float64)
+        out = np.zeros((int(n), 4))
+        self._ck(self.lib.orc_tabulate(jk, _dp(p), len(p), C.c_double(minx), C.c_double(maxx), int(n), _dp(out)))
+        return out
+
     def vmc_step(self, cfg, sigma, Rold, xi_layout, u_m):
         """vmcDriver::step for every chain given the random numbers it consumes."""
         m = self._model(cfg)

@@ -307,6 +307,21 @@ static void radial_eval(const radial *J, double x, double *d0, double *d1, doubl
   *d0 = *d1 = *d2 = 0;
 }
 
+/* jastrow<T>::print (dmc/wavefunction/jastrows/jastrow.h:42-63): rows {x, d0, d1, d2} at the bin centres */
+int orc_tabulate(int kind, const double *p, int np, double minx, double maxx, int n, double *out)
+{
+  radial J;
+  if (radial_init(&J, kind, p, np)) return 1;
+  double deltax = (maxx - minx) / n;
+  for (int i = 0; i < n; i++)
+    {
+      double x = minx + (i + 0.5) * deltax;
+      out[4 * i] = x;
+      radial_eval(&J, x, out + 4 * i + 1, out + 4 * i + 2, out + 4 * i + 3);
+    }
+  return 0;
+}
+
 /* ---- walker with its distance tables (dmc/walkers.h:20-78, dmc/tableDistances.cpp:81-108) ------- */
 typedef struct {
   int a, b;      /* b = -1: one-body table of set a */

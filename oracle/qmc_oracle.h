@@ -64,6 +64,9 @@ int orc_plan(const int *populations, int nRanks, int *sources, int *amounts);
 int orc_update_model(const orc_model *m, double timeStep, int nW, const double *Rold, const double *xi_draw_order,
                      const double *u_m, double *Rout, double *Fout, double *logpsi_out, double *E_out, int *accepted);
 
+/* jastrow<T>::print(minx,maxx,n) (jastrow.h:42-63): n rows {x, u, u', u''}; p = JSON-level parameters of the functor */
+int orc_tabulate(int jastrowKind, const double *p, int np, double minx, double maxx, int n, double *out);
+
 /* one vmcDriver::step (dmc/vmcDriver.cpp:55-84) per chain given xi (draw order) and the Metropolis uniform */
 int orc_vmc_step_model(const orc_model *m, double sigma, int nW, const double *Rold, const double *xi_draw_order,
                        const double *u_m, double *Rout, double *logpsi_out, double *E_out, int *accepted);

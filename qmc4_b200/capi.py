@@ -41,7 +41,7 @@ EXPORTS = [
     "qmc_accumulate_configs", "qmc_upload_walkers", "qmc_download_walkers", "qmc_step",
     "qmc_step_traced", "qmc_block_results", "qmc_get_estimator", "qmc_clear_estimators",
     "qmc_synchronize", "qmc_comm_unique_id", "qmc_comm_init", "qmc_rebalance", "qmc_plan_rebalance",
-    "qmc_get_info", "qmc_stream", "qmc_add_forward_walking", "qmc_set_vmc",
+    "qmc_get_info", "qmc_stream", "qmc_add_forward_walking", "qmc_set_vmc", "qmc_tabulate_wavefunction",
 ]
 FW_INDEX_BASE = 65536
 
@@ -69,6 +69,7 @@ def load():
     lib.qmc_add_forward_walking.argtypes = [vp, C.c_int, C.c_int, c_int_p, C.c_int, c_int_p]
     lib.qmc_set_dmc.argtypes = [vp, C.c_double, C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_int64]
     lib.qmc_set_vmc.argtypes = [vp, C.c_double, C.c_int64, C.c_uint64, C.c_int64]
+    lib.qmc_tabulate_wavefunction.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int64, c_double_p]
     lib.qmc_eval.argtypes = [vp, c_double_p, C.c_int64] + [c_double_p] * 5 + [c_int_p]
     lib.qmc_eval_device.argtypes = [vp, vp, C.c_int64] + [vp] * 6
     lib.qmc_accumulate_configs.argtypes = [vp, c_double_p, C.c_int64]

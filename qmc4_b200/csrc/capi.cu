@@ -1160,6 +1160,22 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
   return 0;
 }
 
+int qmc_tabulate_wavefunction(qmc_ctx *c, int wf_index, double minx, double maxx, int64_t n, double *out)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
+  if (wf_index < 0 || wf_index >= (int)c->wf.size()) return fail(c, "qmc_tabulate_wavefunction: term index out of range");
+  if (n < 1 || !out) return fail(c, "qmc_tabulate_wavefunction: n >= 1 and an output buffer are required");   /* assert(n>=1), jastrow.h:45 */
+  cudaSetDevice(c->device);
+  if (ensure_scratch(c, (size_t)n * 4 * 8, 0)) return 1;
+  CK(launch_tabulate(c->stream, c->wf[wf_index].J, c->coef, minx, (maxx - minx) / (double)n, (long)n, c->scr));
+  c->launches += 1;
+  CK(cudaMemcpyAsync(out, c->scr, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int qmc_set_vmc(qmc_ctx *c, double sigma, int64_t nChains, uint64_t seed, int64_t capacity)
 {
   if (!c) return 1;

@@ -12,6 +12,7 @@
 //                      accumulators.  Population and E_T never leave the device.
 //   eval_kernel      : evaluation of given configurations (parity entry, initial population,
 //                      estimator accumulation over given configurations).
+#include <algorithm>
 #include "kernels.cuh"
 #include "evaluate.cuh"
 #include "kernel_common.cuh"
@@ -414,6 +415,22 @@ __global__ void reduce_hist_kernel(const double *hist, int replicas, int stride,
   out[b] = s;
 }
 
+// jastrow<T>::print (jastrow.h:42-63): u, u', u'' of one radial functor at the n bin centres of [minx, maxx] — the
+// device's own evaluation of the functor, written by the host driver to wave<i>.dat (main.cpp:220-227)
+__global__ void tabulate_kernel(const RadialFn J, const double *coef, double minx, double deltax, long n, double *out)
+{
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    {
+      const double x = minx + ((double)i + 0.5) * deltax;
+      double d0, d1, d2;
+      eval_radial(J, coef, x, d0, d1, d2);
+      out[4 * i + 0] = x;
+      out[4 * i + 1] = d0;
+      out[4 * i + 2] = d1;
+      out[4 * i + 3] = d2;
+    }
+}
+
 // walker (un)packing for migration: slab = count x (2*dofs + 2) doubles  {R, F, logpsi, E}
 __global__ void pack_kernel(WalkerBuf buf, const int *parent, int dofs, int first, int count, double *slab)
 {
@@ -596,6 +613,13 @@ cudaError_t launch_init_identity(cudaStream_t st, int *parent, int *n_desc, int 
 cudaError_t launch_reduce_hist(cudaStream_t st, const double *hist, int replicas, int stride, double *out)
 {
   QMC_LAUNCH(reduce_hist_kernel, (stride + 127) / 128, 128, 0, st, hist, replicas, stride, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tabulate(cudaStream_t st, const RadialFn &J, const double *coef, double minx, double deltax, long n, double *out)
+{
+  if (n <= 0) return cudaSuccess;
+  QMC_LAUNCH(tabulate_kernel, (int)std::min<long>((n + 127) / 128, 1184), 128, 0, st, J, coef, minx, deltax, n, out);
   return cudaGetLastError();
 }
 

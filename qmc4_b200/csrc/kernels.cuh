@@ -88,6 +88,7 @@ cudaError_t launch_scan(cudaStream_t st, const DmcParams &dmc, const StepArgs &a
 cudaError_t launch_finalize_shift(cudaStream_t st, const DmcParams &dmc, Ctl *ctl);
 cudaError_t launch_init_identity(cudaStream_t st, int *parent, int *n_desc, int n, Ctl *ctl);
 cudaError_t launch_reduce_hist(cudaStream_t st, const double *hist, int replicas, int stride, double *out);
+cudaError_t launch_tabulate(cudaStream_t st, const RadialFn &J, const double *coef, double minx, double deltax, long n, double *out);
 cudaError_t launch_pack(cudaStream_t st, const WalkerBuf &buf, const int *parent, int dofs, int first, int count, double *slab);
 cudaError_t launch_unpack(cudaStream_t st, const WalkerBuf &buf, int dofs, int first, int count, const double *slab);
 cudaError_t configure_kernels(int max_smem_optin);

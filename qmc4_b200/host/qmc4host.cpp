@@ -384,6 +384,7 @@ void dmcDriver::run(const std::vector<states_t> &states, size_t nBlocks)
           off += s.size();
         }
     }
+  if (master) writeWaveTables();
   check(qmc_upload_walkers(ctx, R.data(), (int64_t)states.size()));      /* initialize + setEnergyShift (dmcDriver.cpp:163-191) */
   const auto t0 = std::chrono::steady_clock::now();
   for (size_t iBlock = 0; iBlock < nBlocks; ++iBlock)
@@ -436,6 +437,22 @@ void dmcDriver::out(size_t iBlock)
     }
   check(qmc_clear_estimators(ctx));
   dumpConfigurations();
+}
+
+void dmcDriver::writeWaveTables() const
+{ /* main.cpp:220-227: wave<i>.dat = waves[i]->print(), the radial functor tabulated at the bin centres of [0, lBox/2]
+     (jastrow.h:42-63) — here by the device, so the file shows what the kernels evaluate */
+  const real_t half = psi->getGeometry().getLBox(0) / 2.;
+  std::vector<double> tab;
+  for (size_t i = 0; i < psi->waves().size(); ++i)
+    {
+      std::ofstream f("wave" + std::to_string(i) + ".dat");
+      const size_t n = psi->waves()[i]->printPoints();
+      if (n == 0) continue;
+      tab.resize(4 * n);
+      check(qmc_tabulate_wavefunction(ctx, (int)i, 0., half, (int64_t)n, tab.data()));
+      for (size_t k = 0; k < n; ++k) f << tab[4 * k] << " " << tab[4 * k + 1] << " " << tab[4 * k + 2] << " " << tab[4 * k + 3] << std::endl;
+    }
 }
 
 void dmcDriver::dumpConfigurations() const

@@ -113,6 +113,9 @@ class wavefunction {
   const geometry_t &getGeometry() const { return *geo; }
   virtual std::vector<int> sets() const = 0;
   virtual void emit(qmc_ctx *ctx) const = 0;       // device term descriptor
+  // rows of print() = J.print(0, lBox/2, n) (jastrowWavefunctionTwoBody.h:81-83,169: 10000; ...ThreeBody.h:140-144,286-290: 100000;
+  // one-body terms keep wavefunction::print() = "" (wavefunction.h:64))
+  virtual size_t printPoints() const { return 0; }
  protected:
   void add(qmc_ctx *ctx, int wfKind, const std::vector<int> &s, const jastrowBase &J, real_t hs) const;
 
@@ -142,6 +145,7 @@ template <class jastrow_t> class jastrowTwoBodyWavefunctionUndistinguishable : p
   static std::string name() { return "jastrow2bUnDis/" + jastrow_t::name(); }
   std::vector<int> sets() const override { return {setA, setB}; }
   void emit(qmc_ctx *ctx) const override { add(ctx, QMC_WF_JASTROW2B_UNDIS, {setA, setB}, J, -1); }
+  size_t printPoints() const override { return 10000; }
 
  private:
   jastrow_t J;
@@ -158,6 +162,7 @@ template <class jastrow_t> class jastrowTwoBodyWavefunctionDistinguishable : pub
   static std::string name() { return "jastrow2bDis/" + jastrow_t::name(); }
   std::vector<int> sets() const override { return {setA, setB}; }
   void emit(qmc_ctx *ctx) const override { add(ctx, QMC_WF_JASTROW2B_DIS, {setA, setB}, J, -1); }
+  size_t printPoints() const override { return 10000; }
 
  private:
   jastrow_t J;
@@ -173,6 +178,7 @@ template <class jastrow_t> class jastrowThreeBodyWavefunctionUnDistinguishable :
   static std::string name() { return "jastrow3bUnDis/" + jastrow_t::name(); }
   std::vector<int> sets() const override { return {setA, setA}; }
   void emit(qmc_ctx *ctx) const override { add(ctx, QMC_WF_JASTROW3B_UNDIS, {setA}, J, hs); }
+  size_t printPoints() const override { return 100000; }
 
  private:
   jastrow_t J;
@@ -191,6 +197,7 @@ template <class jastrow_t> class jastrowThreeBodyWavefunctionDistinguishable : p
   static std::string name() { return "jastrow3bDis/" + jastrow_t::name(); }
   std::vector<int> sets() const override { return {setA, setB, setC}; }
   void emit(qmc_ctx *ctx) const override { add(ctx, QMC_WF_JASTROW3B_DIS, {setA, setB, setC}, J, hs); }
+  size_t printPoints() const override { return 100000; }
 
  private:
   jastrow_t J;
@@ -572,6 +579,7 @@ class dmcDriver {
   void check(int rc) const;
   void out(size_t iBlock);
   void dumpConfigurations() const;
+  void writeWaveTables() const;
   wavefunction_t *psi;
   potential_t *pot;
   real_t timeStep;

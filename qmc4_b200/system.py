@@ -274,6 +274,12 @@ class System:
                                    _dp(out["V"]), _dp(out["E"]), _ip(out["valid"])))
         return out
 
+    def tabulate_wavefunction(self, index, minx, maxx, n):
+        """jastrow<T>::print (jastrow.h:42-63) evaluated on the device: n rows {x, u, u', u''}"""
+        out = np.zeros((int(n), 4))
+        self._ck(self.lib.qmc_tabulate_wavefunction(self.ctx, int(index), float(minx), float(maxx), int(n), _dp(out)))
+        return out
+
     def accumulate_configs(self, R):
         R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, self.dofs)
         self._ck(self.lib.qmc_accumulate_configs(self.ctx, _dp(R), R.shape[0]))

@@ -327,3 +327,35 @@ def test_vmc_statistical_parity_with_reference_run(tmp_path):
         sa, sb = hd._blocked_error(a), hd._blocked_error(b)
         z = abs(a.mean() - b.mean()) / np.hypot(sa, sb)
         assert z < 3.0, (key, a.mean(), sa, b.mean(), sb)
+
+
+# ---- wave<i>.dat: the radial functors tabulated by the device (main.cpp:220-227, jastrow.h:42-63) -------------
+@pytest.mark.parametrize("name", ["gaussiangaussian", "gaussian"] + sorted(cases.JASTROWS))
+def test_wavefunction_tabulation_vs_oracle(port, name):
+    J = {"gaussiangaussian": cases.GG, "gaussian": {"kind": "gaussian", "alpha": 0.3}}.get(name) or cases.JASTROWS[name]
+    L = 4.0 if name == "hardSphere" else 5.0
+    cfg = cases.pbc(6, L, jastrow=J)
+    s = System.from_input(cfg)
+    got = s.tabulate_wavefunction(0, 0.0, L / 2, 500)
+    s.close()
+    exp = port.tabulate(J, 0.0, L / 2, 500)
+    np.testing.assert_array_equal(got[:, 0], exp[:, 0])
+    ok = np.isfinite(exp).all(axis=1)
+    assert ok.sum() > 100
+    np.testing.assert_array_equal(np.isfinite(got).all(axis=1), ok)
+    for col in (1, 2, 3):
+        assert rel(got[ok, col], exp[ok, col]) < RTOL, col
+
+
+def test_host_driver_writes_wave_tables(tmp_path):
+    """wave<i>.dat per wavefunction term: 10000 rows for two-body terms, 100000 for three-body terms, empty for
+    one-body terms (jastrowWavefunctionTwoBody.h:81-83, jastrowWavefunctionThreeBody.h:140-144, wavefunction.h:64)"""
+    cfg = dict(cases.three_body(N=5, L=3.0), walkers=4, delta_walkers=1, nBlocks=1, stepsPerBlock=1)
+    cfg["wavefunctions"].append({"kind": "jastrow1b", "set": 0, "jastrow": {"kind": "gaussian", "alpha": 0.01}})
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    rows = [len(open(tmp_path / ("wave%d.dat" % i)).read().splitlines()) for i in range(3)]
+    assert rows == [10000, 100000, 0]
+    first = [float(v) for v in open(tmp_path / "wave0.dat").readline().split()]
+    alpha, u0, x = 0.5, -0.5, 0.5 * 1.5 / 10000
+    assert abs(first[0] - x) < 1e-9 and abs(first[1] - u0 * np.exp(-alpha * x * x)) < 1e-5     # jastrowGaussGauss.h:19
