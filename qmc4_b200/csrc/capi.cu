@@ -135,6 +135,7 @@ struct qmc_ctx {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_scan = nullptr, ev_ar = nullptr;
   bool ar_pending = false;
+  int est_occ = 2, est_grid = 0;      // estimator kernel of pipeline 2: resident CTAs per SM it is compiled for, its grid
   double *e_old = nullptr;
   // forward walking (kernels_fw.cu; correlationEstimator.cpp): ring of per-slot histogram rows + ancestor links
   struct FwEst { int target, fw, record_steps; double *sums = nullptr, *weight = nullptr; };
@@ -806,7 +807,7 @@ int one_step_v2(qmc_ctx *c, int accumulate)
     }
   if (accumulate && c->has_hist)
     {
-      CK(launch_estimators(c->cfg, c->stream, c->plan, c->buf[c->cur], c->parent, c->ctl, c->hist));
+      CK(launch_estimators(c->cfg, c->stream, c->plan, c->buf[c->cur], c->parent, c->ctl, c->hist, c->est_occ, c->est_grid));
       c->launches += 1;
     }
   return 0;
@@ -1119,8 +1120,21 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
   if (c->plan.hist_stride > 0)
     {
       c->plan.hist_replicas = c->cfg.grid;
-      CK(cudaMalloc(&c->hist, (size_t)c->cfg.grid * c->plan.hist_stride * 8));
-      CK(cudaMemset(c->hist, 0, (size_t)c->cfg.grid * c->plan.hist_stride * 8));
+      c->est_grid = c->cfg.grid;
+      if (c->pipeline == 2)
+        { /* the estimator kernel of pipeline 2 has its own occupancy target (QMC4_EST_OCC = 2|3|4 resident CTAs per SM) */
+          if (const char *e = getenv("QMC4_EST_OCC"))
+            {
+              const int v = atoi(e);
+              if (v >= 2 && v <= 4) c->est_occ = v;
+            }
+          const int per_sm = std::max(1, std::min(estimator_occupancy(c->est_occ, c->cfg.smem), c->est_occ));
+          const int64_t want = (capacity + c->cfg.groups_per_cta - 1) / c->cfg.groups_per_cta;
+          c->est_grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sms * per_sm));
+          c->plan.hist_replicas = std::max(c->cfg.grid, c->est_grid);
+        }
+      CK(cudaMalloc(&c->hist, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8));
+      CK(cudaMemset(c->hist, 0, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8));
       CK(cudaMalloc(&c->hist_out, (size_t)c->plan.hist_stride * 8));
     }
   if (!c->fw_est.empty())
@@ -1759,6 +1773,8 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "log_down") *value = c->dmc.log_down;
   else if (k == "capacity") *value = (double)c->cap;
   else if (k == "grid") *value = c->cfg.grid;
+  else if (k == "estimator_grid") *value = c->est_grid;
+  else if (k == "estimator_occupancy_target") *value = c->est_occ;
   else if (k == "block") *value = c->cfg.block;
   else if (k == "smem_bytes") *value = (double)c->cfg.smem;
   else if (k == "warps_per_walker") *value = c->cfg.nwarps_per_group;

@@ -104,7 +104,8 @@ cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, cudaStream_t st,
                                 const StepArgs &a, double *e_old);
 cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int n_partials, int multi_rank);
 cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const WalkerBuf &buf, const int *parent,
-                              const Ctl *ctl, double *hist);
+                              const Ctl *ctl, double *hist, int occ, int grid);
+int estimator_occupancy(int occ, size_t smem);
 
 // forward walking (kernels_fw.cu)
 size_t fw_record_group_bytes(const Plan &plan, int max_sf_bins);

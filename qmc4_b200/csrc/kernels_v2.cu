@@ -271,7 +271,10 @@ scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const do
 
 // Estimators over the post-branching population with unit weight per walker (dmcDriver::accumulate,
 // dmcDriver.cpp:257-264): slot j of the new population is walker parent[j] of `buf`.
-__global__ void __launch_bounds__(CTA_THREADS)
+// MINB: resident CTAs per SM the register allocation is bounded for (2: up to 128 registers, 3: 80, 4: 64) — the
+// occupancy experiment of DESIGN.md §4.3 (QMC4_EST_OCC), the histogram pass being latency-bound at 16 warps/SM.
+template <int MINB>
+__global__ void __launch_bounds__(CTA_THREADS, MINB)
 estimator_kernel(const __grid_constant__ Plan plan, const WalkerBuf buf, const int *parent, const Ctl *ctl, double *hist,
                  int nwarps_per_group, size_t group_bytes)
 {
@@ -311,6 +314,18 @@ template <int JK, int VK> const void *prop2() { return (const void *)&prop2_tram
 template <int JK, int VK> const void *prop2() { return (const void *)propagate_v2_kernel<JK, VK>; }
 #endif
 
+#ifdef QMC_EMULATE
+template <int MINB> void est_tramp(void **p)
+{
+  estimator_kernel<MINB>(*(Plan *)p[0], *(WalkerBuf *)p[1], *(const int **)p[2], *(const Ctl **)p[3], *(double **)p[4], *(int *)p[5],
+                         *(size_t *)p[6]);
+}
+template <int MINB> const void *est_fn() { return (const void *)&est_tramp<MINB>; }
+#else
+template <int MINB> const void *est_fn() { return (const void *)estimator_kernel<MINB>; }
+#endif
+const void *est_ptr(int occ) { return occ >= 4 ? est_fn<4>() : occ == 3 ? est_fn<3>() : est_fn<2>(); }
+
 const void *prop2_ptr(int ksel)
 {
   switch (ksel)
@@ -331,7 +346,19 @@ cudaError_t configure_kernels_v2(int max_smem_optin)
       cudaError_t e = cudaFuncSetAttribute(prop2_ptr(k), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
       if (e != cudaSuccess) return e;
     }
-  return cudaFuncSetAttribute((const void *)estimator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+  for (int occ = 2; occ <= 4; ++occ)
+    {
+      cudaError_t e = cudaFuncSetAttribute(est_ptr(occ), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+      if (e != cudaSuccess) return e;
+    }
+  return cudaSuccess;
+}
+
+int estimator_occupancy(int occ, size_t smem)
+{
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, est_ptr(occ), CTA_THREADS, smem) != cudaSuccess) return 1;
+  return n < 1 ? 1 : n;
 }
 
 int propagate_v2_occupancy(int ksel, size_t smem)
@@ -357,12 +384,12 @@ cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs
 }
 
 cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const WalkerBuf &buf, const int *parent,
-                              const Ctl *ctl, double *hist)
+                              const Ctl *ctl, double *hist, int occ, int grid)
 {
   int nw = cfg.nwarps_per_group;
   size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
-  QMC_LAUNCH(estimator_kernel, cfg.grid, cfg.block, cfg.smem, st, plan, buf, parent, ctl, hist, nw, gb);
-  return cudaGetLastError();
+  void *args[] = {(void *)&plan, (void *)&buf, (void *)&parent, (void *)&ctl, (void *)&hist, (void *)&nw, (void *)&gb};
+  return cudaLaunchKernel(est_ptr(occ), dim3(grid), dim3(cfg.block), args, cfg.smem, st);
 }
 
 } // namespace qmc
