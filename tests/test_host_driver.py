@@ -85,9 +85,9 @@ def test_errors_follow_the_reference(tmp_path):
     del cfg["correlationSteps"]
     p = run(cfg, str(tmp_path))
     assert p.returncode != 0 and "correlationSteps" in p.stderr                  # required key (main.cpp:287)
-    cfg = cases.pbc(8, 4.0, walkers=8, method="vmc")
+    cfg = cases.pbc(8, 4.0, walkers=8, method="pigs")
     p = run(cfg, str(tmp_path))
-    assert p.returncode != 0 and "vmc" in p.stderr                               # single-walker VMC stays on the CPU code
+    assert p.returncode != 0 and "method 'pigs'" in p.stderr                     # only dmc / svmc / vmc are device paths
     cfg = cases.pbc(8, 4.0, walkers=8)
     cfg["lBox"] = [4.0, 4.0]
     p = run(cfg, str(tmp_path))
