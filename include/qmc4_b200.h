@@ -157,6 +157,23 @@ int  qmc_add_estimator(qmc_ctx *ctx, int est_kind, const int *sets, int nsets,
 int  qmc_add_forward_walking(qmc_ctx *ctx, int est_index, int record_steps,
                              const int *fw_steps, int n_fw, int *first_index);
 
+/* "superfluidFraction" measurement (estimatorsFactory.cpp:80-116).  Replaces
+ *   createSuperfluidFractionStorer + centerOfMassStorer (correlationEstimator.cpp:187-270,363-410): every walker
+ *     carries a ring of `bins` records {sum_i x_i^d of each stored set}, written at every sampling step, copied
+ *     with the walker by branching (here: one record per surviving slot, found through the ancestor links
+ *     forward walking uses — nothing is copied);
+ *   superfluidFractionEstimator::accumulate (:322-357): for the record j written last and every record i <= j of
+ *     the same turn of the ring, sums[j-i] += sum_d (XA_i - XA_j)(XB_i - XB_j), weights[j-i] += 1, per walker.
+ * setA/setB are species indices (the library stores all species; the factory's remapping through the storer's
+ * set list, :86-108, is not needed).  All measurements must use the same `bins` (the reference derives the record
+ * stride from it, :333).  Index >= QMC_SFL_INDEX_BASE for qmc_get_vector_estimator.  Must precede qmc_set_dmc; not
+ * with qmc_set_vmc (main.cpp:279-282); one rank. */
+#define QMC_SFL_INDEX_BASE 131072
+int  qmc_add_superfluid_fraction(qmc_ctx *ctx, int setA, int setB, int bins, int *est_index);
+/* realVectorAccumulator state of a superfluidFraction estimator since the last qmc_clear_estimators: sums[bins],
+ * weights[bins]; the reference writes "i sums[i]/weights[i]" for weights[i] > 0 (correlationEstimator.cpp:305-320). */
+int  qmc_get_vector_estimator(qmc_ctx *ctx, int est_index, double *sums, double *weights, int bins);
+
 /* dmcDriver constructor arguments + seed + performBranching (dmcDriver.cpp:232-255,
  * main.cpp:363-395).  capacity = walker slots to allocate on this rank (0: 2*(target+delta)/nranks+64).
  * Builds the kernel plan: must follow all qmc_add_* calls. */

@@ -115,6 +115,19 @@ class _Base:
             self._ck(self._fn("forward_walking")(txt, tmp.encode(), _dp(R), _ip(n), _ip(anc), len(n), iEst, _dp(sums), bins, C.byref(w)))
         return sums, w.value
 
+    def superfluid_fraction(self, cfg, pops, ancs, iEst, bins):
+        """the reference's centerOfMassStorer + superfluidFractionEstimator over a genealogy -> (sums, weights)"""
+        txt = json.dumps(cfg).encode()
+        d = _dofs(cfg)
+        n = np.asarray([len(p) for p in pops], dtype=np.int32)
+        R = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, d) for p in pops]))
+        anc = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.int32) for a in ancs]))
+        assert len(anc) == len(R)
+        sums, ws = np.zeros(bins), np.zeros(bins)
+        with tempfile.TemporaryDirectory() as tmp:
+            self._ck(self._fn("superfluid_fraction")(txt, tmp.encode(), _dp(R), _ip(n), _ip(anc), len(n), iEst, _dp(sums), _dp(ws), bins))
+        return sums, ws
+
     def plan(self, populations):
         p = np.asarray(populations, dtype=np.int32)
         src = np.zeros(len(p), dtype=np.int32)
@@ -201,7 +214,7 @@ def flatten(cfg):
         else:
             add(2, kind, p["sets"], 0, [p["functor"]["R0"], p["functor"]["V0"]])
     for e in cfg.get("measurements", []):
-        if e["kind"] in ("energy", "forceEnergy"):
+        if e["kind"] in ("energy", "forceEnergy", "superfluidFraction"):      # no observable term: see Port.superfluid_fraction
             continue
         kind = _EST[e["kind"]]
         if kind == 3:
@@ -337,6 +350,27 @@ class Port(_Base):
         self._ck(self.lib.orc_forward_walking_model(C.byref(m), _dp(R), _ip(n), _ip(anc), len(n), iHist, int(recordSteps),
                                                     int(fwSteps), _dp(sums), bins, C.byref(w)))
         return sums, w.value
+
+    def superfluid_fraction(self, cfg, pops, ancs, iMeas):
+        """iMeas: index among the measurements of the input (a "superfluidFraction" one) -> (sums, weights)"""
+        m = self._model(cfg)
+        d = _dofs(cfg)
+        sf = [x for x in cfg["measurements"] if x["kind"] == "superfluidFraction"]
+        stored = []
+        for x in sf:                                          # createSuperfluidFractionStorer: sets in order of first appearance
+            for s_ in x["sets"]:
+                if s_ not in stored:
+                    stored.append(s_)
+        meas = cfg["measurements"][iMeas]
+        bins = int(meas["bins"])
+        n = np.asarray([len(p) for p in pops], dtype=np.int32)
+        R = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, d) for p in pops]))
+        anc = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.int32) for a in ancs]))
+        st = np.asarray(stored, dtype=np.int32)
+        sums, ws = np.zeros(bins), np.zeros(bins)
+        self._ck(self.lib.orc_superfluid_fraction_model(C.byref(m), _dp(R), _ip(n), _ip(anc), len(n), _ip(st), len(st), int(sf[0]["bins"]),
+                                                        stored.index(meas["sets"][0]), stored.index(meas["sets"][1]), _dp(sums), _dp(ws), bins))
+        return sums, ws
 
     def plan(self, populations):
         p = np.asarray(populations, dtype=np.int32)

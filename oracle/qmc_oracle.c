@@ -1094,6 +1094,90 @@ int orc_forward_walking_model(const orc_model *m, const double *R, const int *n,
   return rc;
 }
 
+/* ---- superfluidFraction (dmc/correlationEstimator.cpp:187-357) ------------------------------------
+ * Same genealogy arguments.  storedSets[nStored]: the sets the centre-of-mass storer keeps, in order of first
+ * appearance over all superfluidFraction measurements (createSuperfluidFractionStorer, :363-410); recordSteps =
+ * the first measurement's "bins" (:199-207); idxA/idxB: positions of the estimator's two sets inside storedSets
+ * (estimatorsFactory.cpp:86-108).  Per walker: data[recordSteps][3*nStored], a time index (the filling flag is
+ * written, never read).  store (:248-268): record i = {sum over particles of each coordinate of each stored set}
+ * — plain coordinates, no minimum image; i = (i+1) % recordSteps.  accumulate (:322-357): recordSize =
+ * data.size()/bins, j = wrapIndex(i-1, bins), for i' = 0..j: W = sum_d (A_i' - A_j)(B_i' - B_j); sums[j-i'] += W;
+ * weights[j-i'] += 1. */
+typedef struct { double *data; int i; } sfl_walker;
+
+int orc_superfluid_fraction_model(const orc_model *m, const double *R, const int *n, const int *anc, int K,
+                                  const int *storedSets, int nStored, int recordSteps, int idxA, int idxB,
+                                  double *sums, double *weights, int bins)
+{
+  int dofs = 0, offs[64];
+  if (m->nSpecies > 64) return fail("too many species");
+  for (int s = 0; s < m->nSpecies; s++) { offs[s] = dofs; dofs += 3 * m->N[s]; }
+  const int width = 3 * nStored;
+  const size_t ring = (size_t)recordSteps * width;
+  const size_t recordSize = ring / bins;                                   /* :333 */
+  for (int b = 0; b < bins; b++) sums[b] = weights[b] = 0;
+  sfl_walker *pop = NULL, *next = NULL;
+  int npop = 0;
+  size_t off = 0;
+  for (int e = 0; e < K; e++)
+    {
+      next = malloc(sizeof(sfl_walker) * (n[e] > 0 ? n[e] : 1));
+      for (int i = 0; i < n[e]; i++)
+        {
+          next[i].data = malloc(sizeof(double) * ring);
+          if (e == 0)
+            {
+              for (size_t k = 0; k < ring; k++) next[i].data[k] = 0;     /* reserve, :209-215 */
+              next[i].i = 0;
+            }
+          else
+            {
+              const sfl_walker *src = pop + anc[off + i];
+              memcpy(next[i].data, src->data, sizeof(double) * ring);
+              next[i].i = src->i;
+            }
+        }
+      for (int i = 0; i < n[e]; i++)
+        {
+          sfl_walker *w = next + i;
+          const double *x = R + (off + i) * dofs;
+          for (int k = 0; k < nStored; k++)
+            {
+              const int s = storedSets[k], N = m->N[s];
+              double xcm[3] = {0, 0, 0};
+              for (int p = 0; p < N; p++)
+                for (int d = 0; d < 3; d++) xcm[d] += x[offs[s] + d * N + p];
+              for (int d = 0; d < 3; d++) w->data[(size_t)w->i * width + 3 * k + d] = xcm[d];
+            }
+          w->i = (w->i + 1) % recordSteps;
+          {
+            int t = w->i - 1;
+            int j = (t >= 0) ? t % bins : bins + t;                        /* wrapIndex, tools.cpp:163-166 */
+            for (int ip = 0; ip <= j; ip++)
+              {
+                double W = 0;
+                for (int d = 0; d < 3; d++)
+                  {
+                    double x1i = w->data[ip * recordSize + 3 * idxA + d], x1j = w->data[j * recordSize + 3 * idxA + d];
+                    double x2i = w->data[ip * recordSize + 3 * idxB + d], x2j = w->data[j * recordSize + 3 * idxB + d];
+                    W += (x1i - x1j) * (x2i - x2j);
+                  }
+                sums[j - ip] += W;
+                weights[j - ip] += 1;
+              }
+          }
+        }
+      for (int i = 0; i < npop; i++) free(pop[i].data);
+      free(pop);
+      pop = next;
+      npop = n[e];
+      off += n[e];
+    }
+  for (int i = 0; i < npop; i++) free(pop[i].data);
+  free(pop);
+  return 0;
+}
+
 /* ---- branching (dmc/branching.cpp) ---------------------------------------------------------------- */
 double orc_energy_shift(const double *E, int n, double timeStep, double meanWalkers_, double deltaWalkers_)
 { /* setEnergyShift (branching.cpp:65-97); meanWalkers/deltaWalkers are size_t members (branching.h:23-24) */

@@ -158,6 +158,41 @@ template <class F> int guarded(F && f)
 
 } // namespace
 
+/* Drives an estimatorCollection over a given genealogy the way dmcDriver does: clones are copies of the ancestor
+ * walker (walkers.cpp:139-179), every walker of every event goes through estimatorCollection::accumulate
+ * (dmcDriver.cpp:257-264: storers first, then estimators). */
+static void run_genealogy(model & m, estimatorCollection & coll, const double * R, const int * n, const int * anc, int K)
+{
+  std::vector<dmcWalker> pop, next;
+  size_t off = 0;
+  for (int e = 0; e < K; e++)
+    {
+      next.clear();
+      next.reserve(n[e]);
+      for (int i = 0; i < n[e]; i++)
+        {
+          if (e == 0)
+            {
+              dmcWalker wk;
+              wk.getStates() = m.unpack(R + (off + i) * m.dofs);
+              initializer::registerDistances(wk.getTableDistances(), *m.psi);
+              initializer::addDistances(wk, coll);
+              coll.reserve(wk);
+              next.push_back(wk);
+            }
+          else
+            {
+              next.push_back(pop.at(anc[off + i]));
+              next.back().getStates() = m.unpack(R + (off + i) * m.dofs);
+            }
+          if (!updateForceGradientEnergy(next.back(), *m.psi, *m.eO)) throw std::runtime_error("invalid configuration");
+        }
+      for (auto & wk : next) coll.accumulate(wk, *m.psi);
+      pop.swap(next);
+      off += n[e];
+    }
+}
+
 extern "C" {
 
 const char * ref_last_error() { return g_err.c_str(); }
@@ -320,34 +355,7 @@ int ref_forward_walking(const char * jsonText, const char * scratchDir, const do
            FIRST block of a reference run is garbage + count.  Every later block starts from
            estimatorCollection::clear() (dmcDriver.cpp:225) — that defined behaviour is what we pin. */
         coll.clear();
-        std::vector<dmcWalker> pop, next;
-        size_t off = 0;
-        for (int e = 0; e < K; e++)
-          {
-            next.clear();
-            next.reserve(n[e]);
-            for (int i = 0; i < n[e]; i++)
-              {
-                if (e == 0)
-                  {
-                    dmcWalker wk;
-                    wk.getStates() = m.unpack(R + (off + i) * m.dofs);
-                    initializer::registerDistances(wk.getTableDistances(), *m.psi);
-                    initializer::addDistances(wk, coll);
-                    coll.reserve(wk);
-                    next.push_back(wk);
-                  }
-                else
-                  {
-                    next.push_back(pop.at(anc[off + i]));
-                    next.back().getStates() = m.unpack(R + (off + i) * m.dofs);
-                  }
-                if (!updateForceGradientEnergy(next.back(), *m.psi, *m.eO)) throw std::runtime_error("invalid configuration");
-              }
-            for (auto & wk : next) coll.accumulate(wk, *m.psi);
-            pop.swap(next);
-            off += n[e];
-          }
+        run_genealogy(m, coll, R, n, anc, K);
         if (auto * sc = dynamic_cast<realScalarForwardWalkingEstimator*>(coll[iEst].get()))
           { /* scalar observable (correlationEstimator.cpp:36-51): accumulator += record; average() = sum/n */
             if (bins != 1) throw std::runtime_error("scalar forward-walking estimator: bins must be 1");
@@ -363,6 +371,37 @@ int ref_forward_walking(const char * jsonText, const char * scratchDir, const do
         if ((int)acc.size() != bins) throw std::runtime_error("bins mismatch");
         for (int i = 0; i < bins; i++) sums[i] = acc.sums()(i);
         *weight = acc.weight();
+      }
+    catch (...) { if (chdir(cwd) != 0) {} throw; }
+    if (chdir(cwd) != 0) throw std::runtime_error("chdir back");
+  });
+}
+
+/* "superfluidFraction" measurements: the reference's centerOfMassStorer + superfluidFractionEstimator
+ * (correlationEstimator.cpp:187-357) created by its own factories (estimatorsFactory.cpp:80-116,
+ * estimatorsFactory.h:90-131) and driven over a genealogy; sums/weights of estimator iEst. */
+int ref_superfluid_fraction(const char * jsonText, const char * scratchDir, const double * R, const int * n,
+                            const int * anc, int K, int iEst, double * sums, double * weights, int bins)
+{
+  return guarded([&] {
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof cwd)) throw std::runtime_error("getcwd");
+    if (chdir(scratchDir) != 0) throw std::runtime_error("chdir scratch");
+    try
+      {
+        model m(jsonText);
+        auto ests = getFactory().createEstimators(m.j["measurements"]);
+        auto storers = getFactory().createStorers(m.j["measurements"]);
+        estimatorCollection coll;
+        for (auto * st : storers) coll.push_back(st);
+        for (auto * e : ests) coll.push_back(e);
+        coll.clear();
+        run_genealogy(m, coll, R, n, anc, K);
+        auto * sf = dynamic_cast<superfluidFractionEstimator*>(coll[iEst].get());
+        if (!sf) throw std::runtime_error("measurement is not a superfluidFraction estimator");
+        auto & acc = sf->getAccumulator();
+        if ((int)acc.size() != bins) throw std::runtime_error("bins mismatch");
+        for (int i = 0; i < bins; i++) { sums[i] = acc.sums()(i); weights[i] = acc.weights()(i); }
       }
     catch (...) { if (chdir(cwd) != 0) {} throw; }
     if (chdir(cwd) != 0) throw std::runtime_error("chdir back");

@@ -141,7 +141,8 @@ struct qmc_ctx {
   struct FwEst { int target, fw, record_steps; double *sums = nullptr, *weight = nullptr; };
   std::vector<FwEst> fw_est;
   int max_sf_bins = 0;
-  int fw_depth = 0;                 // events kept = max(fw)+1
+  int fw_depth = 0;                 // histogram rows kept = max(fw)+1 events
+  int fw_link_depth = 0;            // ancestor links kept = max(fw_depth, superfluid record steps) events
   long fw_event = 0;                // sampling events since the last upload
   double *fw_rows = nullptr;        // [depth][cap][hist_stride]
   int *fw_links = nullptr;          // [depth][cap]  slot at event e -> ancestor slot at event e-1
@@ -150,6 +151,13 @@ struct qmc_ctx {
   int *fw_cnt = nullptr, *fw_nslots = nullptr;
   double *fw_partial = nullptr;
   size_t fw_group_bytes = 0;
+  // superfluidFraction (correlationEstimator.cpp:187-357): ring of per-slot centre-of-mass records on the same event clock
+  struct SflEst { int setA, setB, bins; double *sums = nullptr, *weights = nullptr; };
+  std::vector<SflEst> sfl_est;
+  int sfl_record_steps = 0;         // centerOfMassStorer::recordSteps = "bins" of the first superfluidFraction measurement
+  double *sfl_rec = nullptr;        // [fw_link_depth][cap][3*nSpecies]
+  double *sfl_partial = nullptr;    // [chunks][record_steps]
+  bool genealogy() const { return !fw_est.empty() || !sfl_est.empty(); }
 };
 
 namespace {
@@ -750,7 +758,7 @@ int sync_all(qmc_ctx *c)
 // NEXT step (post-branching walker -> slot of the buffer just written), c->n_desc the descendants per slot.
 int fw_after_step(qmc_ctx *c, int sample)
 {
-  const int cap = (int)c->cap, D = c->fw_depth, stride = c->plan.hist_stride;
+  const int cap = (int)c->cap, D = c->fw_depth, DL = c->fw_link_depth, stride = c->plan.hist_stride;
   const int g = std::max(1, std::min(c->sms * 4, (cap + 255) / 256));
   if (!sample)
     { /* between sampling events the ancestor map is composed with every step's parent map */
@@ -760,21 +768,36 @@ int fw_after_step(qmc_ctx *c, int sample)
       return 0;
     }
   const long e = c->fw_event;
-  const int slot = (int)(e % D);
   if (e > 0)
     {
-      CK(launch_fw_copy_links(c->stream, g, c->fw_comp[c->fw_comp_cur], c->fw_links + (size_t)slot * cap, c->ctl));
+      CK(launch_fw_copy_links(c->stream, g, c->fw_comp[c->fw_comp_cur], c->fw_links + (size_t)(e % DL) * cap, c->ctl));
       c->launches += 1;
     }
-  CK(launch_fw_record(c->stream, std::max(1, std::min(cap, c->sms * 2)), c->fw_group_bytes, c->plan, c->buf[c->cur], c->n_desc, c->ctl,
-                      c->fw_rows + (size_t)slot * cap * stride, c->fw_nslots + slot));
-  c->launches += 1;
+  if (!c->sfl_est.empty())
+    { /* centerOfMassStorer::store, then superfluidFractionEstimator::accumulate (estimatorCollection.cpp:37-49) */
+      const int width = 3 * c->plan.nSpecies, R = c->sfl_record_steps, jmax = (int)(e % R);
+      CK(launch_sfl_record(c->stream, g, c->plan, c->buf[c->cur], c->n_desc, c->ctl, c->sfl_rec + (size_t)(e % DL) * cap * width));
+      c->launches += 1;
+      for (auto &f : c->sfl_est)
+        {
+          CK(launch_sfl_accumulate(c->stream, c->sfl_rec, c->fw_links, c->n_desc, c->ctl, DL, cap, width, e, jmax, 3 * f.setA, 3 * f.setB,
+                                   R, c->sfl_partial, f.sums, f.weights));
+          c->launches += 2;
+        }
+    }
+  const int slot = c->fw_est.empty() ? 0 : (int)(e % D);
+  if (!c->fw_est.empty())
+    {
+      CK(launch_fw_record(c->stream, std::max(1, std::min(cap, c->sms * 2)), c->fw_group_bytes, c->plan, c->buf[c->cur], c->n_desc, c->ctl,
+                          c->fw_rows + (size_t)slot * cap * stride, c->fw_nslots + slot));
+      c->launches += 1;
+    }
   for (auto &f : c->fw_est)
     {
       if (e + 1 < f.record_steps) continue;     /* the walkers' rings are still filling (correlationEstimator.cpp:143) */
       const int tslot = (int)((e - f.fw) % D);
       const Estimator &E = c->plan.est[f.target];
-      CK(launch_fw_accumulate(c->stream, g, c->parent, c->fw_links, D, cap, e, f.fw, c->ctl, c->fw_cnt,
+      CK(launch_fw_accumulate(c->stream, g, c->parent, c->fw_links, DL, cap, e, f.fw, c->ctl, c->fw_cnt,
                               c->fw_rows + (size_t)tslot * cap * stride, c->fw_nslots + tslot, stride, E.offset, E.bins, c->fw_partial,
                               f.sums, f.weight));
       c->launches += 3;
@@ -827,7 +850,7 @@ int one_step(qmc_ctx *c, int accumulate, const TraceDev *tr)
   c->launches += 2;
   c->cur ^= 1;
   if (allreduce_sums(c)) return 1;
-  return c->fw_est.empty() ? 0 : fw_after_step(c, accumulate);
+  return c->genealogy() ? fw_after_step(c, accumulate) : 0;
 }
 
 } // namespace
@@ -969,6 +992,13 @@ void qmc_destroy(qmc_ctx *c)
       cudaFree(f.sums);
       cudaFree(f.weight);
     }
+  cudaFree(c->sfl_rec);
+  cudaFree(c->sfl_partial);
+  for (auto &f : c->sfl_est)
+    {
+      cudaFree(f.sums);
+      cudaFree(f.weights);
+    }
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (int i = 0; i < qmc_ctx::NEV; ++i)
     {
@@ -1059,14 +1089,33 @@ int qmc_add_forward_walking(qmc_ctx *c, int est_index, int record_steps, const i
   return 0;
 }
 
+int qmc_add_superfluid_fraction(qmc_ctx *c, int setA, int setB, int bins, int *est_index)
+{
+  if (!c) return 1;
+  if (c->planned) return fail(c, "superfluidFraction must be declared before qmc_set_dmc");
+  if (setA < 0 || setB < 0 || setA >= (int)c->N.size() || setB >= (int)c->N.size()) return fail(c, "superfluidFraction: set out of range");
+  if (bins < 1) return fail(c, "superfluidFraction: bins >= 1");
+  if (c->sfl_est.empty()) c->sfl_record_steps = bins;       /* createSuperfluidFractionStorer: the first measurement's "bins" (:376-383) */
+  else if (bins != c->sfl_record_steps)
+    /* the reference derives the record size as data.size()/bins (:333): any other value reads the ring with the wrong stride */
+    return fail(c, "superfluidFraction: every measurement must use the same \"bins\" (it is the centre-of-mass storer's recordSteps)");
+  qmc_ctx::SflEst f;
+  f.setA = setA;
+  f.setB = setB;
+  f.bins = bins;
+  if (est_index) *est_index = QMC_SFL_INDEX_BASE + (int)c->sfl_est.size();
+  c->sfl_est.push_back(f);
+  return 0;
+}
+
 int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t deltaWalkers, uint64_t seed,
                 int branching_on, int64_t capacity)
 {
   if (!c) return 1;
   if (c->planned) return fail(c, "qmc_set_dmc called twice");
-  if (!c->fw_est.empty() && c->nranks > 1)
-    return fail(c, "forward walking runs on one GPU in this build: walker records do not migrate between ranks yet");
-  if (!c->fw_est.empty()) c->pipeline = 1;
+  if (c->genealogy() && c->nranks > 1)
+    return fail(c, "forward walking and superfluidFraction run on one GPU in this build: walker records do not migrate between ranks yet");
+  if (c->genealogy()) c->pipeline = 1;
   if (!c->planning_only) cudaSetDevice(c->device);
   if (build_plan(c)) return 1;
   DmcParams &D = c->dmc;
@@ -1137,15 +1186,37 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
       CK(cudaMemset(c->hist, 0, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8));
       CK(cudaMalloc(&c->hist_out, (size_t)c->plan.hist_stride * 8));
     }
+  if (c->genealogy())
+    { /* the event clock both record rings share: ancestor links + the composed parent maps between sampling events */
+      int maxfw = 0;
+      for (auto &f : c->fw_est) maxfw = std::max(maxfw, f.fw);
+      c->fw_depth = maxfw + 1;
+      c->fw_link_depth = std::max(c->fw_depth, c->sfl_record_steps);
+      CK(cudaMalloc(&c->fw_links, (size_t)c->fw_link_depth * capacity * 4));
+      CK(cudaMalloc(&c->fw_comp[0], capacity * 4));
+      CK(cudaMalloc(&c->fw_comp[1], capacity * 4));
+    }
+  if (!c->sfl_est.empty())
+    {
+      const size_t width = 3 * (size_t)c->plan.nSpecies, R = c->sfl_record_steps;
+      const size_t ring = (size_t)c->fw_link_depth * capacity * width * 8;
+      if (cudaMalloc(&c->sfl_rec, ring) != cudaSuccess)
+        return fail(c, "superfluidFraction: cannot allocate the centre-of-mass ring (" + std::to_string(ring >> 20) +
+                           " MiB = bins x capacity x 3 nSpecies x 8 B): fewer walkers or bins");
+      const size_t chunks = (capacity + sfl_chunk_slots() - 1) / sfl_chunk_slots();
+      CK(cudaMalloc(&c->sfl_partial, chunks * R * 8));
+      for (auto &f : c->sfl_est)
+        {
+          CK(cudaMalloc(&f.sums, R * 8));
+          CK(cudaMalloc(&f.weights, R * 8));
+          CK(cudaMemset(f.sums, 0, R * 8));
+          CK(cudaMemset(f.weights, 0, R * 8));
+        }
+    }
   if (!c->fw_est.empty())
     {
-      int maxfw = 0, maxbins = 1;
-      for (auto &f : c->fw_est)
-        {
-          maxfw = std::max(maxfw, f.fw);
-          maxbins = std::max(maxbins, c->plan.est[f.target].bins);
-        }
-      c->fw_depth = maxfw + 1;
+      int maxbins = 1;
+      for (auto &f : c->fw_est) maxbins = std::max(maxbins, c->plan.est[f.target].bins);
       CK(configure_kernels_fw(c->max_smem));
       c->fw_group_bytes = fw_record_group_bytes(c->plan, c->max_sf_bins);
       if (c->fw_group_bytes + (size_t)c->plan.hist_stride * 8 > (size_t)c->max_smem)
@@ -1154,9 +1225,6 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
       if (cudaMalloc(&c->fw_rows, ring) != cudaSuccess)
         return fail(c, "forward walking: cannot allocate the record ring (" + std::to_string(ring >> 20) +
                            " MiB = (max forwardWalkingSteps+1) x capacity x bins x 8 B): fewer walkers, bins or forward-walking steps");
-      CK(cudaMalloc(&c->fw_links, (size_t)c->fw_depth * capacity * 4));
-      CK(cudaMalloc(&c->fw_comp[0], capacity * 4));
-      CK(cudaMalloc(&c->fw_comp[1], capacity * 4));
       CK(cudaMalloc(&c->fw_cnt, capacity * 4));
       CK(cudaMalloc(&c->fw_nslots, (size_t)c->fw_depth * 4));
       CK(cudaMemset(c->fw_nslots, 0, (size_t)c->fw_depth * 4));
@@ -1195,6 +1263,7 @@ int qmc_set_vmc(qmc_ctx *c, double sigma, int64_t nChains, uint64_t seed, int64_
   if (!c) return 1;
   if (!(sigma > 0) || nChains < 1) return fail(c, "qmc_set_vmc: sigma > 0 and at least one chain");
   if (!c->fw_est.empty()) return fail(c, "forward walking needs branching genealogies: use method dmc");
+  if (!c->sfl_est.empty()) return fail(c, "Cannot have vmc and superfluid fraction measurements");        /* main.cpp:279-282 */
   c->pipeline = 1;                      /* the Green-ratio switch lives in propagate_kernel */
   if (capacity <= 0) capacity = nChains / std::max(1, c->nranks) + 64;
   if (qmc_set_dmc(c, sigma, nChains, 0, seed, 0, capacity)) return 1;
@@ -1531,6 +1600,28 @@ int qmc_clear_estimators(qmc_ctx *c)
       CK(cudaMemsetAsync(f.sums, 0, (size_t)c->plan.est[f.target].bins * 8, c->stream));
       CK(cudaMemsetAsync(f.weight, 0, 8, c->stream));
     }
+  for (auto &f : c->sfl_est)
+    {
+      CK(cudaMemsetAsync(f.sums, 0, (size_t)f.bins * 8, c->stream));
+      CK(cudaMemsetAsync(f.weights, 0, (size_t)f.bins * 8, c->stream));
+    }
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+/* superfluidFractionEstimator's realVectorAccumulator: sums[bins] and weights[bins] (accumulators.h, correlationEstimator.cpp:305-320) */
+int qmc_get_vector_estimator(qmc_ctx *c, int est_index, double *sums, double *weights, int bins)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
+  const int k = est_index - QMC_SFL_INDEX_BASE;
+  if (k < 0 || k >= (int)c->sfl_est.size()) return fail(c, "estimator index out of range");
+  const auto &f = c->sfl_est[k];
+  if (bins != f.bins || !sums || !weights) return fail(c, "bins mismatch");
+  cudaSetDevice(c->device);
+  CK(cudaMemcpyAsync(sums, f.sums, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(weights, f.weights, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1767,6 +1858,7 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "hist_stride") *value = c->plan.hist_stride;
   else if (k == "fw_events") *value = (double)c->fw_event;
   else if (k == "fw_depth") *value = c->fw_depth;
+  else if (k == "fw_link_depth") *value = c->fw_link_depth;
   else if (k == "fw_ring_bytes") *value = (double)c->fw_depth * (double)c->cap * c->plan.hist_stride * 8.0;
   else if (k == "groups_per_cta") *value = c->cfg.groups_per_cta;
   else if (k == "log_up") *value = c->dmc.log_up;

@@ -118,5 +118,11 @@ cudaError_t launch_fw_copy_links(cudaStream_t st, int grid, const int *comp, int
 cudaError_t launch_fw_accumulate(cudaStream_t st, int grid, const int *parent, const int *links, int depth, int cap, long event, int fw,
                                  const Ctl *ctl, int *cnt, const double *rows, const int *nslots, int stride, int offset, int bins,
                                  double *partial, double *sums, double *weight);
+// superfluidFraction: centre-of-mass records per surviving slot + lagged winding products along the ancestor links
+int sfl_chunk_slots();
+cudaError_t launch_sfl_record(cudaStream_t st, int grid, const Plan &plan, const WalkerBuf &buf, const int *n_desc, const Ctl *ctl, double *rec);
+cudaError_t launch_sfl_accumulate(cudaStream_t st, const double *rec, const int *links, const int *n_desc, const Ctl *ctl, int depth, int cap,
+                                 int width, long event, int jmax, int offA, int offB, int lag_stride, double *partial, double *sums,
+                                 double *weights);
 
 } // namespace qmc

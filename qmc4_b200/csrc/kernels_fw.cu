@@ -110,6 +110,88 @@ __global__ void fw_finish_kernel(const double *partial, int bins, double *sums, 
   sums[b] += s;
 }
 
+
+// ---- superfluidFraction (correlationEstimator.cpp:187-345) -------------------------------------------------------
+// Reference: centerOfMassStorer keeps, per walker, a ring of `recordSteps` records {sum_i x_i^d of every stored set}
+// (unwrapped coordinates, :222-246), deep-copied with the walker; superfluidFractionEstimator::accumulate (:322-357)
+// adds, for the record j written last and every record i <= j of the SAME turn of the ring,
+// W = sum_d (XA_i - XA_j)(XB_i - XB_j) to bin j-i with weight 1.
+// Here: one record per surviving slot and sampling event (3*nSpecies doubles) in the same event ring as the ancestor
+// links; a slot with n copies in the post-branching population follows its j links once and contributes n*W.
+
+constexpr int SFL_THREADS = 128, SFL_BATCH = 8;
+
+// rec[slot][s*3+d] = sum_i R[slot][off_s + d*N_s + i], summed in particle order like centerOfMassStorer::computeCenterOfMass
+__global__ void sfl_record_kernel(const __grid_constant__ Plan plan, const WalkerBuf buf, const int *n_desc, const Ctl *ctl, double *rec)
+{
+  const int n = ctl->n_prev, width = plan.nSpecies * 3;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < (long)n * width; t += (long)gridDim.x * blockDim.x)
+    {
+      const int j = (int)(t / width), k = (int)(t % width), s = k / 3, d = k % 3;
+      if (n_desc[j] <= 0) continue;
+      const double *x = buf.R + (size_t)j * plan.dofs + plan.off[s] + d * plan.N[s];
+      double acc = 0.0;
+      for (int i = 0; i < plan.N[s]; ++i) acc += x[i];
+      rec[(size_t)j * width + k] = acc;
+    }
+}
+
+// partial[chunk][lag] = sum over the chunk's slots (fixed tree order) of n_desc[slot] * W(lag), lag = 0..jmax
+__global__ void __launch_bounds__(SFL_THREADS)
+sfl_lag_kernel(const double *rec, const int *links, const int *n_desc, const Ctl *ctl, int depth, int cap, int width, long event, int jmax,
+              int offA, int offB, int lag_stride, double *partial)
+{
+  __shared__ double sh[SFL_BATCH][SFL_THREADS];
+  const int n = ctl->n_prev;
+  const int slot = blockIdx.x * SFL_THREADS + threadIdx.x;
+  if (blockIdx.x * SFL_THREADS >= n) return;                       /* uniform per CTA; the finish kernel skips these chunks too */
+  const int m = slot < n ? max(n_desc[slot], 0) : 0;
+  double a0[3] = {0, 0, 0}, b0[3] = {0, 0, 0};
+  if (m)
+    {
+      const double *r0 = rec + ((size_t)(event % depth) * cap + slot) * width;
+      for (int d = 0; d < 3; ++d) { a0[d] = r0[offA + d]; b0[d] = r0[offB + d]; }
+    }
+  int a = slot;
+  for (int base = 0; base <= jmax; base += SFL_BATCH)
+    {
+      const int nb = min(SFL_BATCH, jmax + 1 - base);
+      for (int q = 0; q < nb; ++q)
+        {
+          double W = 0.0;
+          if (m)
+            {
+              const long ev = event - (base + q);
+              const double *r = rec + ((size_t)(ev % depth) * cap + a) * width;
+              for (int d = 0; d < 3; ++d) W += (r[offA + d] - a0[d]) * (r[offB + d] - b0[d]);      /* :343-350 */
+              W *= (double)m;
+              if (base + q < jmax) a = links[(size_t)(ev % depth) * cap + a];   /* ancestor slot one event earlier */
+            }
+          sh[q][threadIdx.x] = W;
+        }
+      __syncthreads();
+      for (int half = SFL_THREADS / 2; half > 0; half >>= 1)
+        {
+          if ((int)threadIdx.x < half)
+            for (int q = 0; q < nb; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + half];
+          __syncthreads();
+        }
+      if ((int)threadIdx.x < nb) partial[(size_t)blockIdx.x * lag_stride + base + threadIdx.x] = sh[threadIdx.x][0];
+      __syncthreads();
+    }
+}
+
+__global__ void sfl_finish_kernel(const double *partial, int lag_stride, int jmax, double *sums, double *weights, const Ctl *ctl)
+{
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > jmax) return;
+  const int chunks = (ctl->n_prev + SFL_THREADS - 1) / SFL_THREADS;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * lag_stride + l];
+  sums[l] += s;
+  weights[l] += (double)ctl->n_cur;                               /* acc.accumulate(W, j-i): weight 1 per walker (:352) */
+}
+
 } // namespace
 
 size_t fw_record_group_bytes(const Plan &plan, int max_sf_bins)
@@ -159,6 +241,25 @@ cudaError_t launch_fw_accumulate(cudaStream_t st, int grid, const int *parent, c
   QMC_LAUNCH(fw_count_kernel, grid, 256, 0, st, parent, links, depth, cap, event, fw, ctl, cnt);
   QMC_LAUNCH(fw_colsum_kernel, dim3(FW_CHUNKS, (bins + 127) / 128), 128, 0, st, rows, cnt, nslots, stride, offset, bins, partial);
   QMC_LAUNCH(fw_finish_kernel, (bins + 127) / 128, 128, 0, st, partial, bins, sums, weight, ctl);
+  return cudaGetLastError();
+}
+
+int sfl_chunk_slots() { return SFL_THREADS; }
+
+cudaError_t launch_sfl_record(cudaStream_t st, int grid, const Plan &plan, const WalkerBuf &buf, const int *n_desc, const Ctl *ctl, double *rec)
+{
+  QMC_LAUNCH(sfl_record_kernel, grid, 256, 0, st, plan, buf, n_desc, ctl, rec);
+  return cudaGetLastError();
+}
+
+// links of event e-l are followed only when lag l+1 is needed, so the unwritten links of event 0 are never read
+cudaError_t launch_sfl_accumulate(cudaStream_t st, const double *rec, const int *links, const int *n_desc, const Ctl *ctl, int depth, int cap,
+                                 int width, long event, int jmax, int offA, int offB, int lag_stride, double *partial, double *sums,
+                                 double *weights)
+{
+  const int chunks = (cap + SFL_THREADS - 1) / SFL_THREADS;
+  QMC_LAUNCH(sfl_lag_kernel, chunks, SFL_THREADS, 0, st, rec, links, n_desc, ctl, depth, cap, width, event, jmax, offA, offB, lag_stride, partial);
+  QMC_LAUNCH(sfl_finish_kernel, (jmax + 128) / 128, 128, 0, st, partial, lag_stride, jmax, sums, weights, ctl);
   return cudaGetLastError();
 }
 

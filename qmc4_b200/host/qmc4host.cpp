@@ -189,6 +189,31 @@ void realScalarForwardWalkingEstimator::write(std::ostream &stream)
   if (n > 0) stream << sum / n;
 }
 
+superfluidFractionEstimator::superfluidFractionEstimator(const json_t &j) : estimatorBase(j["label"].get<std::string>())
+{
+  const json_t &st = j["sets"];
+  if (st.size() != 2) throw invalidInput("Superfluid fraction should have two sets");      /* estimatorsFactory.cpp:88-91 */
+  setA = st[0].get<int>();
+  setB = st[1].get<int>();
+  const size_t bins = j["bins"].get<size_t>();
+  sums.assign(bins, 0);
+  weights.assign(bins, 0);
+  headerIfEmpty("x " + _label);                       /* correlationEstimator.cpp:280-289 */
+}
+void superfluidFractionEstimator::registerOn(qmc_ctx *ctx)
+{
+  rethrow(ctx, qmc_add_superfluid_fraction(ctx, setA, setB, (int)sums.size(), &index));
+}
+void superfluidFractionEstimator::collect(qmc_ctx *ctx, const qmc_block_result &)
+{
+  rethrow(ctx, qmc_get_vector_estimator(ctx, index, sums.data(), weights.data(), (int)sums.size()));
+}
+void superfluidFractionEstimator::write(std::ostream &stream)
+{ /* correlationEstimator.cpp:305-320: lag index and average of the bins that received data, default formatting */
+  for (size_t i = 0; i < sums.size(); i++)
+    if (weights[i] > 0) stream << i << " " << sums[i] / weights[i] << std::endl;
+}
+
 // ---- factory ---------------------------------------------------------------------------------------------
 factory &getFactory()
 {
@@ -276,7 +301,11 @@ std::vector<estimatorBase *> factory::createEstimators(const json_t &j)
             }
           continue;
         }
-      if (id == "superfluidFraction") throw missingImplementation("superfluidFraction is not on the GPU path yet");
+      if (id == "superfluidFraction")
+        { /* estimatorsFactory.cpp:80-116 */
+          out.push_back(new superfluidFractionEstimator(e));
+          continue;
+        }
       if (id == "forceEnergy" || id == "energy") continue;
       auto it = obs.find(id);
       if (it == obs.end()) throw factoryIdNotRecorded(id);

@@ -506,6 +506,23 @@ class realScalarForwardWalkingEstimator : public estimatorBase {   // correlatio
   real_t sum = 0, n = 0;
 };
 
+// superfluidFractionEstimator (correlationEstimator.h:162-180, .cpp:272-357): winding estimator over the centre-of-mass
+// records the walkers carry; on the device the records live per slot on the forward-walking event ring
+// (qmc_add_superfluid_fraction).  Sets are species indices of the input (the factory's remapping through the storer's
+// set list, estimatorsFactory.cpp:86-108, happens inside the library).
+class superfluidFractionEstimator : public estimatorBase {
+ public:
+  explicit superfluidFractionEstimator(const json_t &j);
+  void registerOn(qmc_ctx *ctx) override;
+  void collect(qmc_ctx *ctx, const qmc_block_result &) override;
+  void write(std::ostream &stream) override;
+  std::vector<int> sets() const override { return {setA, setB}; }
+
+ private:
+  int setA, setB, index = -1;
+  std::vector<real_t> sums, weights;
+};
+
 // ---- factory (dmc/factory.h) -------------------------------------------------------------------------
 class factory {
  public:

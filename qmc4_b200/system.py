@@ -191,6 +191,15 @@ class System:
             ek, getsets = _SCALARS[kind]
             sets = np.asarray(getsets(jm), dtype=np.int32)
             self._ck(self.lib.qmc_add_estimator(self.ctx, ek, _ip(sets), len(sets), 1, 0.0, 1.0, None, 0, C.byref(idx)))
+        elif kind == "superfluidFraction":
+            # estimatorsFactory.cpp:80-116: centre-of-mass storer shared by all such measurements + one winding estimator each
+            sets = list(_get(jm, "sets"))
+            if len(sets) != 2:
+                raise invalidInput("Superfluid fraction should have two sets")
+            self._ck(self.lib.qmc_add_superfluid_fraction(self.ctx, int(sets[0]), int(sets[1]), int(_get(jm, "bins")), C.byref(idx)))
+            self.estimators.append(dict(label=_get(jm, "label"), kind=kind, bins=int(jm["bins"]), index=idx.value, scalar=False,
+                                        vector=True, minx=0.0, maxx=0.0))
+            return idx.value
         elif kind == "structureFactor":
             sets = np.asarray(_get(jm, "sets"), dtype=np.int32)
             extra = np.asarray([jm["maxq"], jm["lBox"], jm["channel"]], dtype=np.float64)
@@ -324,6 +333,10 @@ class System:
     def estimator(self, index):
         e = [x for x in self.estimators + self.hidden_estimators if x["index"] == index][0]
         sums = np.zeros(e["bins"])
+        if e.get("vector"):           # realVectorAccumulator: one weight per bin (superfluidFraction)
+            ws = np.zeros(e["bins"])
+            self._ck(self.lib.qmc_get_vector_estimator(self.ctx, index, _dp(sums), _dp(ws), e["bins"]))
+            return sums, ws
         w = C.c_double(0)
         self._ck(self.lib.qmc_get_estimator(self.ctx, index, _dp(sums), e["bins"], C.byref(w)))
         return sums, w.value

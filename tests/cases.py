@@ -191,6 +191,21 @@ def forward_walking_cases():
     return {"pbc_pair": p, "three_body_trimer": t, "mixture_g01": m, "impurity_hyper": h}
 
 
+def superfluid_cases():
+    """"superfluidFraction" measurements (estimatorsFactory.cpp:80-116; centerOfMassStorer + superfluidFractionEstimator,
+    correlationEstimator.cpp:187-357): the winding estimator of one species and the cross term of a mixture.  Every
+    measurement uses the same bins (= the storer's recordSteps, as examples/dmc/dipolarMixture.json does)."""
+    p = pbc(8, 2.2, walkers=24, meas=[{"kind": "superfluidFraction", "label": "rho00", "sets": [0, 0], "bins": 4}])
+    p.update(timeStep=2e-2, delta_walkers=3, seed=13)
+    m = mixture()
+    m.update(N=[4, 5], lBox=[3.0, 3.0, 3.0], timeStep=1e-2, walkers=18, delta_walkers=3)
+    m["measurements"] = [{"kind": "superfluidFraction", "label": "rho11", "sets": [1, 1], "bins": 5},
+                         {"kind": "pairCorrelation", "label": "g01", "sets": [0, 1], "bins": 10, "minx": 0.0, "maxx": 1.5},
+                         {"kind": "superfluidFraction", "label": "rho01", "sets": [0, 1], "bins": 5},
+                         {"kind": "superfluidFraction", "label": "rho00", "sets": [0, 0], "bins": 5}]
+    return {"pbc_rho": p, "mixture_rho": m}
+
+
 def fw_measurement(cfg):
     """(index among the measurements, measurement dict) of the forward-walking measurement of a case"""
     for i, m in enumerate(cfg["measurements"]):

@@ -21,8 +21,28 @@ import cases  # noqa: E402
 from oracle.oracle import REF_BIN, Ref  # noqa: E402
 
 
+def superfluid(ref):
+    """superfluidFraction: the reference's centerOfMassStorer + superfluidFractionEstimator over synthetic genealogies
+    (11 events over rings of 4/5 records) -> superfluid.npz;  `make_golden.py --superfluid` writes only this file"""
+    out = {}
+    for name, cfg in cases.superfluid_cases().items():
+        pops, ancs = cases.synthetic_genealogy(cfg, 11, 6, 2000 + len(name))
+        out[name + "/n"] = np.asarray([len(p_) for p_ in pops])
+        out[name + "/R"] = np.concatenate(pops)
+        out[name + "/anc"] = np.concatenate(ancs)
+        for iM, m_ in enumerate(cfg["measurements"]):          # no forward-walking entries here: estimator index = measurement index
+            if m_["kind"] == "superfluidFraction":
+                sums, ws = ref.superfluid_fraction(cfg, pops, ancs, iM, m_["bins"])
+                out["%s/%s/sums" % (name, m_["label"])] = sums
+                out["%s/%s/weights" % (name, m_["label"])] = ws
+    np.savez_compressed(os.path.join(HERE, "superfluid.npz"), **out)
+
+
 def main():
     ref = Ref()
+    if "--superfluid" in sys.argv:
+        superfluid(ref)
+        return
     rng = np.random.default_rng(424242)
     out = {}
     for name, (cfg, R) in cases.eval_cases().items():
@@ -95,6 +115,8 @@ def main():
             fwd["%s/fw%d/sums" % (name, steps)] = sums
             fwd["%s/fw%d/weight" % (name, steps)] = np.asarray(w)
     np.savez_compressed(os.path.join(HERE, "forward_walking.npz"), **fwd)
+
+    superfluid(ref)
 
     if "--dmc" in sys.argv:
         res = {}

@@ -255,6 +255,41 @@ def test_forward_walking_matches_reference_itself(port, ref):
         np.testing.assert_allclose(b, a, rtol=1e-13, atol=0)
 
 
+SFL = np.load(os.path.join(GOLD, "superfluid.npz")) if os.path.exists(os.path.join(GOLD, "superfluid.npz")) else None
+
+
+@pytest.mark.parametrize("name", sorted(cases.superfluid_cases()))
+def test_superfluid_fraction_matches_golden(port, name):
+    """centre-of-mass ring + winding estimator over a genealogy: the C restatement against what the reference's own
+    centerOfMassStorer / superfluidFractionEstimator produced (bit-equal: same operations in the same order)"""
+    cfg = cases.superfluid_cases()[name]
+    n = SFL[name + "/n"]
+    edges = np.concatenate([[0], np.cumsum(n)])
+    pops = [SFL[name + "/R"][edges[i]:edges[i + 1]] for i in range(len(n))]
+    ancs = [SFL[name + "/anc"][edges[i]:edges[i + 1]] for i in range(len(n))]
+    seen = 0
+    for iM, m in enumerate(cfg["measurements"]):
+        if m["kind"] != "superfluidFraction":
+            continue
+        sums, ws = port.superfluid_fraction(cfg, pops, ancs, iM)
+        np.testing.assert_array_equal(ws, SFL["%s/%s/weights" % (name, m["label"])])
+        np.testing.assert_array_equal(sums, SFL["%s/%s/sums" % (name, m["label"])])
+        assert ws[0] == n.sum() and sums[0] == 0 and ws[-1] > 0
+        seen += 1
+    assert seen >= 1
+
+
+def test_superfluid_fraction_matches_reference_itself(port, ref):
+    cfg = cases.superfluid_cases()["mixture_rho"]
+    pops, ancs = cases.synthetic_genealogy(cfg, 13, 5, 321)
+    for iM, m in enumerate(cfg["measurements"]):
+        if m["kind"] == "superfluidFraction":
+            a, wa = ref.superfluid_fraction(cfg, pops, ancs, iM, m["bins"])
+            b, wb = port.superfluid_fraction(cfg, pops, ancs, iM)
+            np.testing.assert_array_equal(wa, wb)
+            np.testing.assert_array_equal(a, b)
+
+
 def test_forward_walking_needs_steps_below_record_steps(port):
     cfg = cases.forward_walking_cases()["pbc_pair"]
     pops, ancs = cases.synthetic_genealogy(cfg, 3, 4, 1)

@@ -86,6 +86,84 @@ def test_forward_walking_ring_restarts_with_a_new_population(port):
     s.close()
 
 
+# ---- superfluidFraction (centerOfMassStorer + superfluidFractionEstimator on the ancestor links) ----------------
+@pytest.mark.parametrize("sample_every", [1, 2])
+@pytest.mark.parametrize("name", sorted(cases.superfluid_cases()))
+def test_superfluid_fraction_vs_oracle_on_the_traced_genealogy(port, name, sample_every):
+    """per-slot centre-of-mass records + link hops against the per-walker rings the reference copies at every branching;
+    11 events over rings of 4/5 records: the ring turns over twice, so the restart of the lags at record 0 is covered"""
+    cfg = cases.superfluid_cases()[name]
+    s = System.from_input(cfg)
+    bins = [m["bins"] for m in cfg["measurements"] if m["kind"] == "superfluidFraction"][0]
+    assert s.info("fw_link_depth") == bins
+    pops, ancs = _traced_genealogy(s, cfg, 11, sample_every, np.random.default_rng(5))
+    assert len({len(p) for p in pops}) > 1, "no branching happened: the test would not exercise the genealogy"
+    by_label = {e["label"]: e for e in s.estimators}
+    for iM, m in enumerate(cfg["measurements"]):
+        if m["kind"] != "superfluidFraction":
+            continue
+        got, w = s.estimator(by_label[m["label"]]["index"])
+        exp, we = port.superfluid_fraction(cfg, pops, ancs, iM)
+        np.testing.assert_array_equal(w, we)
+        assert w[0] > w[-1] > 0
+        assert rel(got, exp) < RTOL, m["label"]
+    s.clear_estimators()
+    got, w = s.estimator(by_label[[m for m in cfg["measurements"] if m["kind"] == "superfluidFraction"][0]["label"]]["index"])
+    assert not w.any() and not got.any()
+    s.close()
+
+
+def test_superfluid_fraction_without_branching_and_errors(port):
+    """svmc (branching off, main.cpp:393-395): identity genealogy; the record clock restarts with a new population;
+    vmc + superfluidFraction is invalidInput in the reference (main.cpp:279-282); bins must agree (the storer's recordSteps)"""
+    cfg = dict(cases.superfluid_cases()["pbc_rho"], method="svmc")
+    s = System.from_input(cfg)
+    rng = np.random.default_rng(2)
+    _traced_genealogy(s, cfg, 3, 1, rng)
+    s.clear_estimators()
+    pops, ancs = _traced_genealogy(s, cfg, 6, 1, rng)
+    assert len({len(p) for p in pops}) == 1
+    got, w = s.estimator(s.estimators[0]["index"])
+    exp, we = port.superfluid_fraction(cfg, pops, ancs, 0)
+    np.testing.assert_array_equal(w, we)
+    assert rel(got, exp) < RTOL
+    s.close()
+    with pytest.raises(Exception, match="vmc and superfluid"):
+        System.from_input(dict(cfg, method="vmc"))
+    bad = cases.superfluid_cases()["mixture_rho"]
+    bad["measurements"][2]["bins"] = 7
+    with pytest.raises(Exception, match="same .bins"):
+        System.from_input(bad)
+    bad = cases.superfluid_cases()["pbc_rho"]
+    bad["measurements"][0]["sets"] = [0]
+    with pytest.raises(Exception, match="two sets"):
+        System.from_input(bad)
+
+
+def test_superfluid_fraction_measurement_file(tmp_path):
+    """<label>.dat of the host driver (superfluidFractionEstimator::write, correlationEstimator.cpp:305-320): header
+    "x <label>", per block the rows "lag average" of the lags that received data.  Physics check: the pair Jastrow's
+    drift sums to zero over the particles, so the centre of mass diffuses freely, W(lag) = <(sum_i dx_i)^2> = 3 N tau lag
+    x acceptance (superfluid fraction 1 for this translation-invariant gas)."""
+    cfg = cases.superfluid_cases()["pbc_rho"]
+    cfg = dict(cfg, stepsPerBlock=8, nBlocks=3, correlationSteps=0, walkers=40, delta_walkers=6)
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    m = cfg["measurements"][0]
+    txt = open(tmp_path / (m["label"] + ".dat")).read()
+    lines = txt.split("\n")
+    assert lines[0] == "x " + m["label"]
+    blocks = [[r for r in b.split("\n") if r.strip()] for b in txt[len(lines[0]) + 1:].split("\n\n")]
+    blocks = [b for b in blocks if b]
+    assert len(blocks) == 3 and all(len(b) == m["bins"] for b in blocks)
+    vals = np.array([[[float(v) for v in r.split()] for r in b] for b in blocks])
+    np.testing.assert_array_equal(vals[:, :, 0], np.tile(np.arange(m["bins"]), (3, 1)))
+    assert (vals[:, 0, 1] == 0).all()                                         # lag 0: a record against itself
+    W = vals[:, :, 1].mean(axis=0)
+    free = 3 * cfg["N"][0] * cfg["timeStep"] * np.arange(m["bins"])
+    assert np.all(np.abs(W[1:] / free[1:] - 1) < 0.35), (W, free)
+
+
 def test_forward_walking_errors():
     cfg = cases.structure_factor()
     cfg["measurements"][0].update(recordSteps=4, forwardWalkingSteps=[1])
