@@ -157,6 +157,15 @@ int  qmc_add_estimator(qmc_ctx *ctx, int est_kind, const int *sets, int nsets,
 int  qmc_add_forward_walking(qmc_ctx *ctx, int est_index, int record_steps,
                              const int *fw_steps, int n_fw, int *first_index);
 
+/* "forceEnergy" measurement (main.cpp:270-273: realScalarEstimator("forceEnergy", new forceEnergy(&pot)), attached to
+ * vmcDriver (:318-335) and to dmcDriver for svmc only (:395-408)).  forceEnergy::operator() (energy.cpp:37-61) =
+ * 0.5 * sum_i |grad_i log psi|^2 + V of every walker at every sampling step, weight 1.  Device: one extra evaluation
+ * launch + reduction per sampling step, outside the hot kernels.  Must precede qmc_set_dmc(branching_on = 0) /
+ * qmc_set_vmc; qmc_set_dmc with branching fails, as the reference never attaches it there.
+ * qmc_get_force_energy: {sum, count} since the last qmc_clear_estimators (reduced over ranks). */
+int  qmc_enable_force_energy(qmc_ctx *ctx);
+int  qmc_get_force_energy(qmc_ctx *ctx, double *sum, double *count);
+
 /* "superfluidFraction" measurement (estimatorsFactory.cpp:80-116).  Replaces
  *   createSuperfluidFractionStorer + centerOfMassStorer (correlationEstimator.cpp:187-270,363-410): every walker
  *     carries a ring of `bins` records {sum_i x_i^d of each stored set}, written at every sampling step, copied

@@ -115,6 +115,14 @@ class _Base:
             self._ck(self._fn("forward_walking")(txt, tmp.encode(), _dp(R), _ip(n), _ip(anc), len(n), iEst, _dp(sums), bins, C.byref(w)))
         return sums, w.value
 
+    def force_energy(self, cfg, R):
+        """forceEnergy::operator() per configuration (energy.cpp:37-61)"""
+        txt = json.dumps(cfg).encode()
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, _dofs(cfg))
+        out = np.zeros(R.shape[0])
+        self._ck(self._fn("force_energy")(txt, _dp(R), R.shape[0], _dp(out)))
+        return out
+
     def superfluid_fraction(self, cfg, pops, ancs, iEst, bins):
         """the reference's centerOfMassStorer + superfluidFractionEstimator over a genealogy -> (sums, weights)"""
         txt = json.dumps(cfg).encode()
@@ -350,6 +358,13 @@ class Port(_Base):
         self._ck(self.lib.orc_forward_walking_model(C.byref(m), _dp(R), _ip(n), _ip(anc), len(n), iHist, int(recordSteps),
                                                     int(fwSteps), _dp(sums), bins, C.byref(w)))
         return sums, w.value
+
+    def force_energy(self, cfg, R):
+        m = self._model(cfg)
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, _dofs(cfg))
+        out = np.zeros(R.shape[0])
+        self._ck(self.lib.orc_force_energy_model(C.byref(m), _dp(R), R.shape[0], _dp(out)))
+        return out
 
     def superfluid_fraction(self, cfg, pops, ancs, iMeas):
         """iMeas: index among the measurements of the input (a "superfluidFraction" one) -> (sums, weights)"""

@@ -1094,6 +1094,37 @@ int orc_forward_walking_model(const orc_model *m, const double *R, const int *n,
   return rc;
 }
 
+/* ---- forceEnergy (dmc/energy.cpp:37-61) -------------------------------------------------------------
+ * evaluateDerivatives, then ef = sum over sets of (grad.array()*grad.array()).sum() (Eigen reduces a column-major
+ * N x 3 array; the order of that reduction is Eigen's, so agreement with the reference is to rounding, not bit-equal),
+ * no phase gradients for Jastrow-only wavefunctions; returns 0.5*ef + V. */
+int orc_force_energy_model(const orc_model *m, const double *R, int nW, double *out)
+{
+  int dofs = 0;
+  for (int s = 0; s < m->nSpecies; s++) dofs += 3 * m->N[s];
+  double *grad = malloc(sizeof(double) * (size_t)nW * dofs), *V = malloc(sizeof(double) * nW);
+  int *valid = malloc(sizeof(int) * nW);
+  int rc = orc_eval_model(m, R, nW, NULL, grad, NULL, V, NULL, valid);
+  for (int w = 0; w < nW && !rc; w++)
+    {
+      if (!valid[w]) { rc = fail("invalid configuration"); break; }
+      double ef = 0;
+      size_t off = 0;
+      for (int s = 0; s < m->nSpecies; s++)
+        {
+          double tmp = 0;
+          for (int k = 0; k < 3 * m->N[s]; k++) tmp += grad[(size_t)w * dofs + off + k] * grad[(size_t)w * dofs + off + k];
+          ef += tmp;
+          off += 3 * m->N[s];
+        }
+      out[w] = 0.5 * ef + V[w];
+    }
+  free(grad);
+  free(V);
+  free(valid);
+  return rc;
+}
+
 /* ---- superfluidFraction (dmc/correlationEstimator.cpp:187-357) ------------------------------------
  * Same genealogy arguments.  storedSets[nStored]: the sets the centre-of-mass storer keeps, in order of first
  * appearance over all superfluidFraction measurements (createSuperfluidFractionStorer, :363-410); recordSteps =

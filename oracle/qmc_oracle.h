@@ -52,6 +52,7 @@ int orc_drift_diffuse_model(const orc_model *m, double timeStep, int nW, const d
 int orc_histogram_model(const orc_model *m, const double *R, int nW, int iEst, double *sums, int bins, double *weight);
 int orc_forward_walking_model(const orc_model *m, const double *R, const int *n, const int *anc, int K, int iEst,
                               int recordSteps, int fwSteps, double *sums, int bins, double *weight);
+int orc_force_energy_model(const orc_model *m, const double *R, int nW, double *out);
 int orc_superfluid_fraction_model(const orc_model *m, const double *R, const int *n, const int *anc, int K,
                                   const int *storedSets, int nStored, int recordSteps, int idxA, int idxB,
                                   double *sums, double *weights, int bins);

@@ -377,6 +377,22 @@ int ref_forward_walking(const char * jsonText, const char * scratchDir, const do
   });
 }
 
+/* forceEnergy::operator() (dmc/energy.cpp:37-61) of the reference on nW configurations: out[nW]. */
+int ref_force_energy(const char * jsonText, const double * R, int nW, double * out)
+{
+  return guarded([&] {
+    model m(jsonText);
+    forceEnergy fe(m.pot.get());
+    for (int w = 0; w < nW; w++)
+      {
+        dmcWalker wk;
+        auto st = m.unpack(R + (size_t)w * m.dofs);
+        if (!initializer::initialize(wk, st, *m.psi, *m.eO)) throw std::runtime_error("invalid configuration");
+        out[w] = fe(wk, *m.psi);
+      }
+  });
+}
+
 /* "superfluidFraction" measurements: the reference's centerOfMassStorer + superfluidFractionEstimator
  * (correlationEstimator.cpp:187-357) created by its own factories (estimatorsFactory.cpp:80-116,
  * estimatorsFactory.h:90-131) and driven over a genealogy; sums/weights of estimator iEst. */

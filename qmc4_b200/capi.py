@@ -42,7 +42,7 @@ EXPORTS = [
     "qmc_step_traced", "qmc_block_results", "qmc_get_estimator", "qmc_clear_estimators",
     "qmc_synchronize", "qmc_comm_unique_id", "qmc_comm_init", "qmc_rebalance", "qmc_plan_rebalance",
     "qmc_get_info", "qmc_stream", "qmc_add_forward_walking", "qmc_set_vmc", "qmc_tabulate_wavefunction",
-    "qmc_add_superfluid_fraction", "qmc_get_vector_estimator",
+    "qmc_add_superfluid_fraction", "qmc_get_vector_estimator", "qmc_enable_force_energy", "qmc_get_force_energy",
 ]
 FW_INDEX_BASE = 65536
 SFL_INDEX_BASE = 131072
@@ -71,6 +71,8 @@ def load():
     lib.qmc_add_forward_walking.argtypes = [vp, C.c_int, C.c_int, c_int_p, C.c_int, c_int_p]
     lib.qmc_add_superfluid_fraction.argtypes = [vp, C.c_int, C.c_int, C.c_int, c_int_p]
     lib.qmc_get_vector_estimator.argtypes = [vp, C.c_int, c_double_p, c_double_p, C.c_int]
+    lib.qmc_enable_force_energy.argtypes = [vp]
+    lib.qmc_get_force_energy.argtypes = [vp, c_double_p, c_double_p]
     lib.qmc_set_dmc.argtypes = [vp, C.c_double, C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_int64]
     lib.qmc_set_vmc.argtypes = [vp, C.c_double, C.c_int64, C.c_uint64, C.c_int64]
     lib.qmc_tabulate_wavefunction.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int64, c_double_p]

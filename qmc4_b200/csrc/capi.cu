@@ -158,6 +158,10 @@ struct qmc_ctx {
   double *sfl_rec = nullptr;        // [fw_link_depth][cap][3*nSpecies]
   double *sfl_partial = nullptr;    // [chunks][record_steps]
   bool genealogy() const { return !fw_est.empty() || !sfl_est.empty(); }
+  // forceEnergy (energy.cpp:37-61) for the methods without branching (main.cpp:318-335,395-408): a cold pass per sampling step
+  bool force_energy = false;
+  int64_t n_host = 0;               // population known to the host: constant while branching is off
+  double *fe_R = nullptr, *fe_F = nullptr, *fe_V = nullptr, *fe_partial = nullptr, *fe_acc = nullptr;   // fe_acc = {sum, count}
 };
 
 namespace {
@@ -836,6 +840,8 @@ int one_step_v2(qmc_ctx *c, int accumulate)
   return 0;
 }
 
+int force_energy_pass(qmc_ctx *c);
+
 int one_step(qmc_ctx *c, int accumulate, const TraceDev *tr)
 {
   if (c->pipeline == 2 && !tr) return one_step_v2(c, accumulate);
@@ -850,6 +856,7 @@ int one_step(qmc_ctx *c, int accumulate, const TraceDev *tr)
   c->launches += 2;
   c->cur ^= 1;
   if (allreduce_sums(c)) return 1;
+  if (accumulate && c->force_energy && force_energy_pass(c)) return 1;
   return c->genealogy() ? fw_after_step(c, accumulate) : 0;
 }
 
@@ -863,6 +870,65 @@ __global__ void gather_kernel(WalkerBuf buf, const int *parent, int dofs, int co
   for (int k = threadIdx.x; k < dofs; k += blockDim.x) R[(size_t)w * dofs + k] = buf.R[(size_t)p * dofs + k];
   if (threadIdx.x == 0 && E) E[w] = buf.E[p];
 }
+
+// forceEnergy::operator() (energy.cpp:37-61): 0.5 * sum |grad log psi|^2 + V per walker; per-CTA running sums in a fixed order
+constexpr int FE_THREADS = 128, FE_BLOCKS = 64;
+__global__ void __launch_bounds__(FE_THREADS) force_energy_kernel(const double *F, const double *V, int dofs, int n, double *partial)
+{
+  __shared__ double sh[FE_THREADS];
+  double total = 0.0;
+  for (int w = blockIdx.x; w < n; w += gridDim.x)
+    {
+      double s = 0.0;
+      for (int k = threadIdx.x; k < dofs; k += FE_THREADS)
+        {
+          const double f = F[(size_t)w * dofs + k];
+          s += f * f;
+        }
+      sh[threadIdx.x] = s;
+      __syncthreads();
+      for (int h = FE_THREADS / 2; h > 0; h >>= 1)
+        {
+          if ((int)threadIdx.x < h) sh[threadIdx.x] += sh[threadIdx.x + h];
+          __syncthreads();
+        }
+      if (threadIdx.x == 0) total += 0.5 * sh[0] + V[w];
+      __syncthreads();
+    }
+  if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+__global__ void force_energy_finish_kernel(const double *partial, int nb, int n, double *acc)
+{
+  if (threadIdx.x) return;
+  double s = 0.0;
+  for (int b = 0; b < nb; ++b) s += partial[b];
+  acc[0] += s;
+  acc[1] += (double)n;
+}
+
+extern "C" {
+static int eval_common(qmc_ctx *c, const double *dR, int64_t nW, double *dlogpsi, double *dgrad, double *dlap,
+                       double *dV, double *dE, int *dvalid, bool hist, int flag_invalid);
+}
+namespace {
+
+// the observable re-evaluates the derivatives of the walker it is given (psi.evaluateDerivatives, energy.cpp:42): gather the
+// population through the parent map, one evaluation launch, one reduction.  Never on the DMC path (branching on).
+int force_energy_pass(qmc_ctx *c)
+{
+  const int n = (int)c->n_host, dofs = c->plan.dofs;
+  if (n < 1) return 0;
+  QMC_LAUNCH(gather_kernel, n, 128, 0, c->stream, c->buf[c->cur], c->parent, dofs, n, c->fe_R, (double *)nullptr);
+  CK(cudaGetLastError());
+  if (eval_common(c, c->fe_R, n, nullptr, c->fe_F, nullptr, c->fe_V, nullptr, nullptr, false, 0)) return 1;
+  const int nb = std::min(n, FE_BLOCKS);
+  QMC_LAUNCH(force_energy_kernel, nb, FE_THREADS, 0, c->stream, c->fe_F, c->fe_V, dofs, n, c->fe_partial);
+  QMC_LAUNCH(force_energy_finish_kernel, 1, 32, 0, c->stream, c->fe_partial, nb, n, c->fe_acc);
+  CK(cudaGetLastError());
+  c->launches += 3;
+  return 0;
+}
+} // namespace
 
 // ================================================================================================
 extern "C" {
@@ -992,6 +1058,11 @@ void qmc_destroy(qmc_ctx *c)
       cudaFree(f.sums);
       cudaFree(f.weight);
     }
+  cudaFree(c->fe_R);
+  cudaFree(c->fe_F);
+  cudaFree(c->fe_V);
+  cudaFree(c->fe_partial);
+  cudaFree(c->fe_acc);
   cudaFree(c->sfl_rec);
   cudaFree(c->sfl_partial);
   for (auto &f : c->sfl_est)
@@ -1089,6 +1160,36 @@ int qmc_add_forward_walking(qmc_ctx *c, int est_index, int record_steps, const i
   return 0;
 }
 
+int qmc_enable_force_energy(qmc_ctx *c)
+{
+  if (!c) return 1;
+  if (c->planned) return fail(c, "forceEnergy must be declared before qmc_set_dmc / qmc_set_vmc");
+  c->force_energy = true;
+  return 0;
+}
+
+int qmc_get_force_energy(qmc_ctx *c, double *sum, double *count)
+{
+  if (!c) return 1;
+  if (!c->planned) return fail(c, "qmc_set_dmc must be called first");
+  if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
+  if (!c->force_energy) return fail(c, "forceEnergy was not enabled (qmc_enable_force_energy)");
+  cudaSetDevice(c->device);
+  double h[2] = {0, 0};
+  if (c->nranks > 1)
+    { /* estimator::accumulateMPI: reduced over the ranks */
+      if (ensure_scratch(c, 64, 0)) return 1;
+      CK(cudaMemcpyAsync(c->scr, c->fe_acc, 16, cudaMemcpyDeviceToDevice, c->stream));
+      NK(g_nccl.AllReduce(c->scr, c->scr, 2, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+      CK(cudaMemcpyAsync(h, c->scr, 16, cudaMemcpyDeviceToHost, c->stream));
+    }
+  else CK(cudaMemcpyAsync(h, c->fe_acc, 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (sum) *sum = h[0];
+  if (count) *count = h[1];
+  return 0;
+}
+
 int qmc_add_superfluid_fraction(qmc_ctx *c, int setA, int setB, int bins, int *est_index)
 {
   if (!c) return 1;
@@ -1115,7 +1216,10 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
   if (c->planned) return fail(c, "qmc_set_dmc called twice");
   if (c->genealogy() && c->nranks > 1)
     return fail(c, "forward walking and superfluidFraction run on one GPU in this build: walker records do not migrate between ranks yet");
-  if (c->genealogy()) c->pipeline = 1;
+  if (c->genealogy() || c->force_energy) c->pipeline = 1;
+  if (c->force_energy && branching_on)
+    /* main.cpp attaches the forceEnergy estimator to vmcDriver (:318-335) and to dmcDriver only for svmc (:395-408) */
+    return fail(c, "forceEnergy is measured by the methods without branching (vmc, svmc), as in the reference");
   if (!c->planning_only) cudaSetDevice(c->device);
   if (build_plan(c)) return 1;
   DmcParams &D = c->dmc;
@@ -1185,6 +1289,15 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
       CK(cudaMalloc(&c->hist, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8));
       CK(cudaMemset(c->hist, 0, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8));
       CK(cudaMalloc(&c->hist_out, (size_t)c->plan.hist_stride * 8));
+    }
+  if (c->force_energy)
+    {
+      CK(cudaMalloc(&c->fe_R, capacity * c->plan.dofs * 8));
+      CK(cudaMalloc(&c->fe_F, capacity * c->plan.dofs * 8));
+      CK(cudaMalloc(&c->fe_V, capacity * 8));
+      CK(cudaMalloc(&c->fe_partial, FE_BLOCKS * 8));
+      CK(cudaMalloc(&c->fe_acc, 16));
+      CK(cudaMemset(c->fe_acc, 0, 16));
     }
   if (c->genealogy())
     { /* the event clock both record rings share: ancestor links + the composed parent maps between sampling events */
@@ -1368,6 +1481,7 @@ int qmc_upload_walkers(qmc_ctx *c, const double *R, int64_t nW)
   if (nW < 1) return fail(c, "need at least one walker");
   if (nW > c->cap) return fail(c, "more walkers than capacity");
   c->fw_event = 0;                     /* a new population starts with empty records (storer::reserve) */
+  c->n_host = nW;
   const size_t dofs = c->plan.dofs;
   WalkerBuf &B = c->buf[c->cur];
   CK(cudaMemcpyAsync(B.R, R, nW * dofs * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1600,6 +1714,7 @@ int qmc_clear_estimators(qmc_ctx *c)
       CK(cudaMemsetAsync(f.sums, 0, (size_t)c->plan.est[f.target].bins * 8, c->stream));
       CK(cudaMemsetAsync(f.weight, 0, 8, c->stream));
     }
+  if (c->fe_acc) CK(cudaMemsetAsync(c->fe_acc, 0, 16, c->stream));
   for (auto &f : c->sfl_est)
     {
       CK(cudaMemsetAsync(f.sums, 0, (size_t)f.bins * 8, c->stream));
@@ -1773,6 +1888,7 @@ int qmc_rebalance(qmc_ctx *c, int64_t *moved)
     }
   int np = h.n_prev + n_recv;
   CK(cudaMemcpyAsync(&c->ctl->n_cur, &n_cur, 4, cudaMemcpyHostToDevice, c->stream));
+  c->n_host = n_cur;
   CK(cudaMemcpyAsync(&c->ctl->n_prev, &np, 4, cudaMemcpyHostToDevice, c->stream));
   double newpop = n_cur;
   CK(cudaMemcpyAsync(&c->ctl->gsum[2 + c->rank], &newpop, 8, cudaMemcpyHostToDevice, c->stream));

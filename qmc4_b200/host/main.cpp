@@ -98,6 +98,15 @@ static void runRank(const json_t &j, int rank, int nranks, const void *uid, int 
       dmcO.getRandomGenerator().seed((unsigned long long)seed + rank);
       if (method == "svmc") dmcO.disableBranching();
       if (vmc) dmcO.enableVmc();
+      /* main.cpp:270-273,318-335,395-408: the forceEnergy estimator always exists (its file gets the header), it is attached
+         for vmc and svmc only, before the estimators of "measurements" */
+      std::unique_ptr<forceEnergyEstimator> m2(new forceEnergyEstimator);
+      if (rank == 0) m2->writeHeaderNow();
+      bool wantForceEnergy = false;
+      if (j.contains("measurements"))
+        for (const json_t &m : j["measurements"].elements())
+          if (m["kind"].get<std::string>() == "forceEnergy") wantForceEnergy = true;
+      if (wantForceEnergy && (vmc || method == "svmc")) dmcO.getEstimators().push_back(m2.release());   /* the driver owns its estimators */
       for (auto *e : ests) dmcO.getEstimators().push_back(e);
       dmcO.run(dmcStates, nBlocks);
       for (auto *w : waves) delete w;

@@ -189,6 +189,21 @@ void realScalarForwardWalkingEstimator::write(std::ostream &stream)
   if (n > 0) stream << sum / n;
 }
 
+forceEnergyEstimator::forceEnergyEstimator() : estimatorBase("forceEnergy") { headerIfEmpty(_label); }
+void forceEnergyEstimator::writeHeaderNow()
+{
+  if (pendingHeader.empty()) return;
+  f << pendingHeader << std::endl;
+  pendingHeader.clear();
+}
+void forceEnergyEstimator::registerOn(qmc_ctx *ctx) { rethrow(ctx, qmc_enable_force_energy(ctx)); }
+void forceEnergyEstimator::collect(qmc_ctx *ctx, const qmc_block_result &) { rethrow(ctx, qmc_get_force_energy(ctx, &sum, &n)); }
+void forceEnergyEstimator::write(std::ostream &stream)
+{ /* realScalarEstimator::write (estimators.cpp:89-98) */
+  stream << std::scientific << std::setprecision(12);
+  if (n > 0) stream << sum / n;
+}
+
 superfluidFractionEstimator::superfluidFractionEstimator(const json_t &j) : estimatorBase(j["label"].get<std::string>())
 {
   const json_t &st = j["sets"];

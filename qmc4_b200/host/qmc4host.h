@@ -506,6 +506,21 @@ class realScalarForwardWalkingEstimator : public estimatorBase {   // correlatio
   real_t sum = 0, n = 0;
 };
 
+// main.cpp:270-273: realScalarEstimator("forceEnergy", new forceEnergy(&pot)) — always constructed (so forceEnergy.dat always
+// gets its header on rank 0), attached to the driver only for vmc (:318-335) and svmc (:395-408) when "measurements" has a
+// {"kind": "forceEnergy"} entry.  forceEnergy::operator() (energy.cpp:37-61) runs on the device (qmc_enable_force_energy).
+class forceEnergyEstimator : public estimatorBase {
+ public:
+  forceEnergyEstimator();
+  void writeHeaderNow();                                        // estimators.cpp:35-46 (rank 0, at construction)
+  void registerOn(qmc_ctx *ctx) override;
+  void collect(qmc_ctx *ctx, const qmc_block_result &) override;
+  void write(std::ostream &stream) override;
+
+ private:
+  real_t sum = 0, n = 0;
+};
+
 // superfluidFractionEstimator (correlationEstimator.h:162-180, .cpp:272-357): winding estimator over the centre-of-mass
 // records the walkers carry; on the device the records live per slot on the forward-walking event ring
 // (qmc_add_superfluid_fraction).  Sets are species indices of the input (the factory's remapping through the storer's

@@ -264,6 +264,10 @@ class System:
             s.comm_init(*comm)
         method = j.get("method", "dmc")
         walkers = int(j.get("walkers", 1))
+        # main.cpp:318-335,395-408: the forceEnergy estimator is attached for vmc and svmc only (ignored for dmc, as there)
+        s.force_energy_enabled = method in ("vmc", "svmc") and any(m.get("kind") == "forceEnergy" for m in j.get("measurements", []))
+        if s.force_energy_enabled:
+            s._ck(s.lib.qmc_enable_force_energy(s.ctx))
         if method == "vmc":          # vmcDriver(&psi, timeStep) (main.cpp:314): "walkers" independent chains on the GPU
             s.set_vmc(j.get("timeStep", 1e-3), walkers, seed=int(j.get("seed", 0)), capacity=capacity)
             s.input = j
@@ -340,6 +344,12 @@ class System:
         w = C.c_double(0)
         self._ck(self.lib.qmc_get_estimator(self.ctx, index, _dp(sums), e["bins"], C.byref(w)))
         return sums, w.value
+
+    def force_energy(self):
+        """(sum, count) of forceEnergy::operator() over the walkers of the sampling steps since the last clear"""
+        a, n = C.c_double(0), C.c_double(0)
+        self._ck(self.lib.qmc_get_force_energy(self.ctx, C.byref(a), C.byref(n)))
+        return a.value, n.value
 
     def clear_estimators(self):
         self._ck(self.lib.qmc_clear_estimators(self.ctx))

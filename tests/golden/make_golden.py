@@ -38,10 +38,26 @@ def superfluid(ref):
     np.savez_compressed(os.path.join(HERE, "superfluid.npz"), **out)
 
 
+def force_energy(ref):
+    """forceEnergy::operator() (energy.cpp:37-61) of the reference on the evaluation cases -> force_energy.npz"""
+    out = {}
+    for name in ("pbc_gg_barrier_N33", "mixture", "trap_N10", "three_body"):
+        if name not in cases.eval_cases():
+            continue
+        cfg, R = cases.eval_cases()[name]
+        R = R[ref.eval(cfg, R)["valid"] == 1]
+        out[name + "/R"] = R
+        out[name + "/forceEnergy"] = ref.force_energy(cfg, R)
+    np.savez_compressed(os.path.join(HERE, "force_energy.npz"), **out)
+
+
 def main():
     ref = Ref()
-    if "--superfluid" in sys.argv:
-        superfluid(ref)
+    if "--superfluid" in sys.argv or "--force-energy" in sys.argv:
+        if "--superfluid" in sys.argv:
+            superfluid(ref)
+        if "--force-energy" in sys.argv:
+            force_energy(ref)
         return
     rng = np.random.default_rng(424242)
     out = {}
@@ -117,6 +133,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "forward_walking.npz"), **fwd)
 
     superfluid(ref)
+    force_energy(ref)
 
     if "--dmc" in sys.argv:
         res = {}

@@ -290,6 +290,20 @@ def test_superfluid_fraction_matches_reference_itself(port, ref):
             np.testing.assert_array_equal(a, b)
 
 
+def test_force_energy_matches_golden(port):
+    """0.5 sum |grad log psi|^2 + V: the restatement against forceEnergy::operator() of the reference (energy.cpp:37-61);
+    Eigen's reduction order differs from a plain loop, hence 1e-13 instead of bit-equality"""
+    G = np.load(os.path.join(GOLD, "force_energy.npz"))
+    names = sorted({k.split("/")[0] for k in G.files})
+    assert len(names) >= 3
+    for name in names:
+        cfg, _ = cases.eval_cases()[name]
+        got = port.force_energy(cfg, G[name + "/R"])
+        np.testing.assert_allclose(got, G[name + "/forceEnergy"], rtol=1e-13, atol=0)
+        ev = port.eval(cfg, G[name + "/R"])
+        np.testing.assert_allclose(got, 0.5 * (ev["grad"] ** 2).sum(axis=1) + ev["V"], rtol=1e-13)
+
+
 def test_forward_walking_needs_steps_below_record_steps(port):
     cfg = cases.forward_walking_cases()["pbc_pair"]
     pops, ancs = cases.synthetic_genealogy(cfg, 3, 4, 1)

@@ -390,6 +390,69 @@ def test_host_driver_vmc_block_report_and_files(tmp_path):
     assert len(json.load(open(tmp_path / "configurations" / "walkers-Rank0.json"))["configurations"]) == 1
 
 
+# ---- forceEnergy (energy.cpp:37-61; attached for vmc and svmc, main.cpp:318-335,395-408) ----------------------
+@pytest.mark.parametrize("method", ["svmc", "vmc"])
+@pytest.mark.parametrize("name", ["pbc_gg_barrier_N33", "mixture", "trap_N10"])
+def test_force_energy_vs_oracle_on_traced_steps(port, name, method):
+    """0.5 sum |grad log psi|^2 + V of every walker after every sampling step (accepted or carried-through), against the
+    oracle's forceEnergy::operator() on the downloaded populations; sampling every 2nd step"""
+    cfg, R = cases.eval_cases()[name]
+    R = R[port.eval(cfg, R)["valid"] == 1][:12]
+    cfg = dict(cfg, method=method, walkers=len(R), timeStep=0.05 if method == "vmc" else 5e-3,
+               measurements=list(cfg.get("measurements", [])) + [{"kind": "forceEnergy", "label": "forceEnergy"}])
+    s = System.from_input(cfg)
+    s.upload(R)
+    exp_sum, exp_n, rejected = 0.0, 0, 0
+    for t in range(6):
+        sample = t % 2 == 1
+        tr = s.step_traced(accumulate=sample)
+        rejected += int((tr["accepted"][:len(R)] == 0).sum())
+        if sample:
+            Rnow, _ = s.download(with_energy=True)
+            assert len(Rnow) == len(R)
+            exp_sum += port.force_energy(cfg, Rnow).sum()
+            exp_n += len(Rnow)
+    got, n = s.force_energy()
+    assert n == exp_n and abs(got - exp_sum) < RTOL * abs(exp_sum)
+    s.clear_estimators()
+    assert s.force_energy() == (0.0, 0.0)
+    s.close()
+    # method dmc: the reference never attaches the estimator (main.cpp:395-408) -> the measurement is ignored; asking the
+    # library for it with branching on is an error
+    s = System.from_input(dict(cfg, method="dmc"))
+    assert not s.force_energy_enabled
+    with pytest.raises(Exception, match="not enabled"):
+        s.force_energy()
+    s.close()
+    s = System(cfg["lBox"], cfg["N"])
+    for jw in cfg["wavefunctions"]:
+        s.add_wavefunction(jw)
+    s._ck(s.lib.qmc_enable_force_energy(s.ctx))
+    with pytest.raises(Exception, match="without branching"):
+        s.set_dmc(1e-3, 10)
+    s.close()
+
+
+def test_host_driver_force_energy_file(tmp_path):
+    """forceEnergy.dat: header always (main.cpp:273 constructs the estimator unconditionally), one %.12e average per block
+    for svmc with a {"kind": "forceEnergy"} measurement, header only for dmc.  Under |psi|^2 sampling <forceEnergy> =
+    <E_L> (integration by parts), so for the harmonic trap both sit near the variational energy."""
+    cfg = dict(cases.vmc_case(), walkers=16, stepsPerBlock=20, nBlocks=4, correlationSteps=1)
+    cfg["measurements"] = cfg["measurements"] + [{"kind": "forceEnergy", "label": "forceEnergy"}]
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    lines = open(tmp_path / "forceEnergy.dat").read().split("\n")
+    assert lines[0] == "forceEnergy"
+    fe = np.array([float(x) for x in lines[1:] if x.strip()])
+    e = np.loadtxt(tmp_path / "energy.dat", skiprows=1)
+    assert len(fe) == 4 and len(e) == 4 and np.isfinite(fe).all()
+    assert abs(fe.mean() - e.mean()) < 0.25 * abs(e.mean())
+    os.remove(tmp_path / "forceEnergy.dat")
+    p = hd.run(dict(cfg, method="dmc", walkers=16, timeStep=1e-3, stepsPerBlock=3, nBlocks=2), str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    assert open(tmp_path / "forceEnergy.dat").read().strip() == "forceEnergy"
+
+
 @pytest.mark.skipif(hd.BIN.endswith("_emu"), reason="statistics need ~1e7 chain steps: hardware only")
 def test_vmc_statistical_parity_with_reference_run(tmp_path):
     """parity (2) for the VMC leg of BASELINE config 1: variational energy and <cm2> of 512 GPU chains against the
