@@ -44,7 +44,9 @@ enum qmc_jastrow_kind {
   QMC_J_SQUAREWELL_BOUND = 8,/* "squareWellBoundState" {V0,R0,Rm,cut_off,aInverse,eb,alpha} jastrowSquareWell.h:80-150 */
   QMC_J_DELTA_PHONONS = 9,   /* "delta_phonons"   {k,delta,beta,z,cut_off}       jastrow_delta.h:4-54 (g is parsed, unused: process() is never called) */
   QMC_J_DELTA_IN_TRAP = 10,  /* "delta_in_trap"   {a}                            jastrow_delta.h:56-72         */
-  QMC_J_DELTA_BOUND_STATE_PHONONS = 11 /* "delta_bound_state_phonons" {xI,k,A,beta,cut_off} jastrow_delta.h:74-98 */
+  QMC_J_DELTA_BOUND_STATE_PHONONS = 11,/* "delta_bound_state_phonons" {xI,k,A,beta,cut_off} jastrow_delta.h:74-98 */
+  QMC_J_DIPOLAR_REP = 12     /* "dipolar_rep"     {D,cut_off,matching_point,alpha,C}  jastrowDipolar.h:9-73 (Bessel K_n on the
+                                device instead of boost::math::cyl_bessel_k; see DESIGN.md for how it is pinned) */
 };
 
 /* ---- wavefunction terms (dmc/wavefunction/) ------------------------------------------------- */

@@ -177,7 +177,8 @@ _J = {"gaussian": (1, ("alpha",)), "gaussiangaussian": (2, ("r0", "u0")),
       "hardSphere": (7, ("a", "k", "cut_off")),
       "squareWellBoundState": (8, ("V0", "R0", "Rm", "cut_off", "aInverse", "eb", "alpha")),
       "delta_phonons": (9, ("k", "delta", "beta", "z", "cut_off")), "delta_in_trap": (10, ("a",)),
-      "delta_bound_state_phonons": (11, ("xI", "k", "A", "beta", "cut_off"))}
+      "delta_bound_state_phonons": (11, ("xI", "k", "A", "beta", "cut_off")),
+      "dipolar_rep": (12, ("D", "cut_off", "matching_point", "alpha", "C"))}
 _WF = {"jastrow1b": 1, "jastrow2bUnDis": 2, "jastrow2bDis": 3, "jastrow3bUnDis": 4, "jastrow3bDis": 5}
 _POT = {"harmonic1b": 1, "squareWell2b": 2, "dipolar2b": 3, "poschTeller2b": 4, "potentialTwoBody/squareWell": 5,
         "potentialTwoBody/potentialBarrier": 6, "potentialThreeBodyUnDis/squareWell": 7,

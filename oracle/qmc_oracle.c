@@ -9,6 +9,7 @@
  * against the golden vectors in tests/golden/ produced by the reference.
  */
 #include "qmc_oracle.h"
+#include "bessel_k.h"
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -96,6 +97,14 @@ static int radial_init(radial *J, int kind, const double *p, int np)
     case ORC_J_DELTA_IN_TRAP: J->a[0] = p[0]; return 0;      /* jastrow_delta.cpp:71-74 */
     case ORC_J_DELTA_BOUND_STATE_PHONONS: /* jastrow_delta.cpp:76-86; p = {xI,k,A,beta,cut_off} */
       J->a[0] = p[0]; J->a[1] = p[1]; J->a[2] = log(p[2]); J->a[3] = p[3]; J->a[4] = M_PI / (p[4] * 2);
+      return 0;
+    case ORC_J_DIPOLAR_REP: /* jastrowDipolar.cpp:3-27; p = {D,cut_off,matching_point,alpha,C} as in the input */
+      J->a[0] = sqrt(p[0]);            /* D = sqrt(j["D"]) */
+      J->a[1] = p[1] * 2;              /* lBox = cut_off*2 */
+      J->a[2] = p[2];                  /* matching_point */
+      J->a[3] = p[3];                  /* alpha */
+      J->a[4] = M_PI / J->a[1];        /* k = pi/lBox */
+      J->a[5] = log(p[4]);             /* logC */
       return 0;
     case ORC_J_BSPLINE: /* jastrowSpline.cpp:20-78; p = {stepSize,valueRight,derivativeRight,c...} */
       J->a[0] = 1. / p[0];
@@ -264,6 +273,31 @@ static void radial_eval(const radial *J, double x, double *d0, double *d1, doubl
         *d0 = (x < xI) ? -k * x : logA + log(pow(sin(k2 * x), beta));
         *d1 = (x < xI) ? -k : beta * k2 / tan(k2 * x);
         *d2 = (x < xI) ? 0 : -k2 * beta * k2 / pow(sin(k2 * x), 2);
+        return;
+      }
+    case ORC_J_DIPOLAR_REP: /* jastrowDipolar.h:21-62 */
+      {
+        const double D = a[0], lBox = a[1], mp = a[2], alpha = a[3], k = a[4], logC = a[5];
+        if (x < mp)
+          {
+            double sq = sqrt(x), y = 2 * D / sq;
+            double J1 = orc_cyl_bessel_k(1, y), K0 = orc_cyl_bessel_k(0, y), K2 = orc_cyl_bessel_k(2, y);
+            double K3 = orc_cyl_bessel_k(3, y), Km1 = orc_cyl_bessel_k(-1, y);
+            *d0 = log(sq * J1) + logC;
+            double Jp = -(K2 + K0) / 2.;
+            Jp /= J1;
+            *d1 = 0.5 / x * (1 - Jp * y);
+            double Jp2 = (K3 + Km1 + 2 * J1) / 4.;
+            Jp2 = Jp2 / J1;
+            *d2 = (-1 + y * Jp * 3 / 2. + 0.5 * y * y * (Jp2 - Jp * Jp)) / (2 * x * x);
+          }
+        else if (x <= lBox / 2.)
+          {
+            *d0 = alpha * log(sin(k * x));
+            *d1 = alpha * k * 1. / tan(k * x);
+            *d2 = -alpha * k * k / pow(sin(k * x), 2);
+          }
+        else *d0 = *d1 = *d2 = 0;
         return;
       }
     case ORC_J_BSPLINE: /* jastrowSpline.cpp:80-110 */
@@ -1093,6 +1127,10 @@ int orc_forward_walking_model(const orc_model *m, const double *R, const int *n,
   free(tmp);
   return rc;
 }
+
+/* exported for the scipy pin of oracle/bessel_k.h */
+double orc_bessel_k(int n, double x) { return orc_cyl_bessel_k(n, x); }
+void orc_bessel_k01e(double x, double *k0, double *k1) { orc_bessel_k01_scaled(x, k0, k1); }
 
 /* ---- forceEnergy (dmc/energy.cpp:37-61) -------------------------------------------------------------
  * evaluateDerivatives, then ef = sum over sets of (grad.array()*grad.array()).sum() (Eigen reduces a column-major

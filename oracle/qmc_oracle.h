@@ -24,7 +24,7 @@ extern "C" {
 
 enum { ORC_J_GAUSSIAN = 1, ORC_J_GAUSSGAUSS, ORC_J_SQUAREWELL, ORC_J_HARDSPHEREGAUSS, ORC_J_BSPLINE,
        ORC_J_POSCHTELLER, ORC_J_HARDSPHERE, ORC_J_SQUAREWELL_BOUND,
-       ORC_J_DELTA_PHONONS, ORC_J_DELTA_IN_TRAP, ORC_J_DELTA_BOUND_STATE_PHONONS };
+       ORC_J_DELTA_PHONONS, ORC_J_DELTA_IN_TRAP, ORC_J_DELTA_BOUND_STATE_PHONONS, ORC_J_DIPOLAR_REP };
 enum { ORC_WF_JASTROW1B = 1, ORC_WF_JASTROW2B_UNDIS, ORC_WF_JASTROW2B_DIS, ORC_WF_JASTROW3B_UNDIS, ORC_WF_JASTROW3B_DIS };
 enum { ORC_POT_HARMONIC1B = 1, ORC_POT_SQUAREWELL2B, ORC_POT_DIPOLAR2B, ORC_POT_POSCHTELLER2B,
        ORC_POT_TWOBODY_SQUAREWELL, ORC_POT_TWOBODY_BARRIER, ORC_POT_THREEBODY_UNDIS_SQUAREWELL,
@@ -52,6 +52,8 @@ int orc_drift_diffuse_model(const orc_model *m, double timeStep, int nW, const d
 int orc_histogram_model(const orc_model *m, const double *R, int nW, int iEst, double *sums, int bins, double *weight);
 int orc_forward_walking_model(const orc_model *m, const double *R, const int *n, const int *anc, int K, int iEst,
                               int recordSteps, int fwSteps, double *sums, int bins, double *weight);
+double orc_bessel_k(int n, double x);
+void orc_bessel_k01e(double x, double *k0, double *k1);
 int orc_force_energy_model(const orc_model *m, const double *R, int nW, double *out);
 int orc_superfluid_fraction_model(const orc_model *m, const double *R, const int *n, const int *anc, int K,
                                   const int *storedSets, int nStored, int recordSteps, int idxA, int idxB,

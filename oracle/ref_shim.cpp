@@ -37,6 +37,7 @@
 #include "wavefunction/jastrows/jastrowGaussian.h"
 #include "wavefunction/jastrows/jastrowGaussGauss.h"
 #include "wavefunction/jastrows/jastrowHardSphereGauss.h"
+#include "wavefunction/jastrows/jastrowDipolar.h"
 #include "ptools.h"
 #include "pairCorrelation.h"
 #include "centerOfMassSquared.h"
@@ -61,8 +62,8 @@ void registerAllOnce()
   static bool done = false;
   if (done) return;
   done = true;
-  /* same registrations as dmc/main.cpp:188-216,236-243 minus dipolar_rep (needs Boost) and the
-     fermionic orbitals (out of scope) */
+  /* same registrations as dmc/main.cpp:188-216,236-243 minus the fermionic orbitals (out of scope); dipolar_rep runs on
+     the Bessel stand-in of oracle/stubs/boost (oracle/bessel_k.h) */
   auto & f = getFactory();
   f.registerJastrow<gaussianJastrow>();
   f.registerJastrow<jastrowGaussGauss>();
@@ -75,6 +76,7 @@ void registerAllOnce()
   f.registerJastrow<jastrow_delta_phonons>();
   f.registerJastrow<jastrow_delta_in_trap>();
   f.registerJastrow<jastrow_delta_bound_state_phonons>();
+  f.registerJastrow<jastrowDipolarRep>();
   f.registerObservable<pairCorrelation>();
   f.registerObservable<centerOfMassSquared>();
   f.registerObservable<trimerhyperRadius>();

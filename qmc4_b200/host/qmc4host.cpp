@@ -248,6 +248,7 @@ void registerDefaults(factory &f)
   f.registerJastrow<jastrow_delta_phonons>();                /* main.cpp:213-215 */
   f.registerJastrow<jastrow_delta_in_trap>();
   f.registerJastrow<jastrow_delta_bound_state_phonons>();
+  f.registerJastrow<jastrowDipolarRep>();                    /* main.cpp:216 */
   f.registerObservable<pairCorrelation>();
   f.registerObservable<trimerCorrelationUnDis>();
   f.registerObservable<structureFactor>();

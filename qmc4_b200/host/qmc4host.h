@@ -67,6 +67,7 @@ QMC_JASTROW(jastrowPoschTeller, "poschTeller", QMC_J_POSCHTELLER, "R0", "C", "al
 QMC_JASTROW(jastrowHardSphereGauss, "hardSphereGauss", QMC_J_HARDSPHEREGAUSS, "a", "Rm", "D");
 QMC_JASTROW(jastrowHardSphere, "hardSphere", QMC_J_HARDSPHERE, "a", "k", "cut_off");
 QMC_JASTROW(jastrow_delta_in_trap, "delta_in_trap", QMC_J_DELTA_IN_TRAP, "a");                        // jastrow_delta.cpp:71-74
+QMC_JASTROW(jastrowDipolarRep, "dipolar_rep", QMC_J_DIPOLAR_REP, "D", "cut_off", "matching_point", "alpha", "C");   // jastrowDipolar.cpp:3-13
 #undef QMC_JASTROW
 struct jastrow_delta_phonons : jastrowBase {                                                          // jastrow_delta.cpp:5-39
   static std::string name() { return "delta_phonons"; }

@@ -73,6 +73,7 @@ _JASTROWS = {
     "squareWellBoundState": (capi.J_SQUAREWELL_BOUND, lambda j: [_get(j, k) for k in ("V0", "R0", "Rm", "cut_off", "aInverse", "eb", "alpha")]),
     "delta_phonons": (capi.J_DELTA_PHONONS, lambda j: _delta_phonons(j)),
     "delta_in_trap": (capi.J_DELTA_IN_TRAP, lambda j: [_get(j, "a")]),
+    "dipolar_rep": (capi.J_DIPOLAR_REP, lambda j: [_get(j, k) for k in ("D", "cut_off", "matching_point", "alpha", "C")]),   # jastrowDipolar.cpp:3-13
     "delta_bound_state_phonons": (capi.J_DELTA_BOUND_STATE_PHONONS, lambda j: _delta_bound_state(j)),
 }
 _WAVES = {"jastrow1b": capi.WF_JASTROW1B, "jastrow2bUnDis": capi.WF_JASTROW2B_UNDIS,

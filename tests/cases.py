@@ -82,7 +82,8 @@ def impurity(N=(6, 5, 1), L=4.0):
                              {"kind": "centerOfMassSquared", "label": "cm2", "set": 0}]}
 
 
-NEW_PATH_EVAL_CASES = ("mixture3", "mixture3_hs", "impurity")     # GPU-tested from tests/test_zz_gpu_new_paths.py
+DIPOLAR_REP = {"kind": "dipolar_rep", "D": 1.3, "cut_off": 2.5, "matching_point": 1.4, "alpha": 0.6, "C": 0.8}
+NEW_PATH_EVAL_CASES = ("mixture3", "mixture3_hs", "impurity", "jastrow_dipolar_rep")     # GPU-tested from tests/test_zz_gpu_new_paths.py
 
 
 def three_set_hist_cases():
@@ -145,6 +146,8 @@ def eval_cases():
     out["mixture3"] = (mixture3(), rng.uniform(-2.0, 2.0, size=(6, 36)))
     out["mixture3_hs"] = (mixture3(hs=1.3), rng.uniform(-2.0, 2.0, size=(12, 36)))
     out["impurity"] = (impurity(), rng.uniform(-2.0, 2.0, size=(6, 36)))
+    # dipolar_rep (jastrowDipolar.h: Bessel-K branch below matching_point, sin^alpha tail up to cut_off, flat beyond)
+    out["jastrow_dipolar_rep"] = (pbc(18, 5.2, jastrow=DIPOLAR_REP), rng.uniform(-2.6, 2.6, size=(6, 54)))
     return out
 
 

@@ -290,6 +290,24 @@ def test_superfluid_fraction_matches_reference_itself(port, ref):
             np.testing.assert_array_equal(a, b)
 
 
+def test_bessel_k_pinned_on_scipy(port):
+    """oracle/bessel_k.h (the Boost.Math stand-in behind the reference's dipolar_rep code in oracle/_ref, and the oracle's
+    own restatement) against an independent implementation: scipy.special.kve / kv (AMOS).  Boost itself is absent, so this
+    is the pin for that Jastrow's special function; the rest of jastrowDipolar.h is the reference's own compiled code."""
+    import ctypes as C
+    from scipy.special import kv, kve
+    port.lib.orc_bessel_k.restype = C.c_double
+    port.lib.orc_bessel_k.argtypes = [C.c_int, C.c_double]
+    port.lib.orc_bessel_k01e.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    k0, k1 = C.c_double(0), C.c_double(0)
+    for x in np.concatenate([np.logspace(-4, np.log10(700.0), 1500), np.linspace(0.05, 12, 400)]):
+        port.lib.orc_bessel_k01e(float(x), C.byref(k0), C.byref(k1))
+        assert abs(k0.value / kve(0, x) - 1) < 4e-15 and abs(k1.value / kve(1, x) - 1) < 4e-15, x
+    for x in np.logspace(-3, np.log10(50.0), 300):
+        for n in (0, 1, 2, 3, -1):
+            assert abs(port.lib.orc_bessel_k(n, float(x)) / kv(abs(n), x) - 1) < 2e-14, (n, x)
+
+
 def test_force_energy_matches_golden(port):
     """0.5 sum |grad log psi|^2 + V: the restatement against forceEnergy::operator() of the reference (energy.cpp:37-61);
     Eigen's reduction order differs from a plain loop, hence 1e-13 instead of bit-equality"""
