@@ -153,8 +153,9 @@ int  qmc_add_estimator(qmc_ctx *ctx, int est_kind, const int *sets, int nsets,
  * The n_fw estimators get the indices *first_index .. *first_index+n_fw-1 (>= QMC_FW_INDEX_BASE) for
  * qmc_get_estimator.  Must precede qmc_set_dmc.  Errors: vector observables (structure factor) have
  * no forward-walking estimator in the reference either (missingImplementation, :68);
- * fw >= recordSteps (assert, correlationEstimator.cpp:137); more than one rank (records do not
- * migrate yet). */
+ * fw >= recordSteps (assert, correlationEstimator.cpp:137).  With a communicator qmc_rebalance ships the lineage records
+ * of the migrating walkers with them (the reference's walker messages carry the rings, walkers.cpp:181-233) and
+ * qmc_get_estimator returns the sums reduced over the ranks. */
 #define QMC_FW_INDEX_BASE 65536
 int  qmc_add_forward_walking(qmc_ctx *ctx, int est_index, int record_steps,
                              const int *fw_steps, int n_fw, int *first_index);
@@ -178,7 +179,7 @@ int  qmc_get_force_energy(qmc_ctx *ctx, double *sum, double *count);
  * setA/setB are species indices (the library stores all species; the factory's remapping through the storer's
  * set list, :86-108, is not needed).  All measurements must use the same `bins` (the reference derives the record
  * stride from it, :333).  Index >= QMC_SFL_INDEX_BASE for qmc_get_vector_estimator.  Must precede qmc_set_dmc; not
- * with qmc_set_vmc (main.cpp:279-282); one rank. */
+ * with qmc_set_vmc (main.cpp:279-282).  Multi-rank: records migrate in qmc_rebalance, results are reduced over ranks. */
 #define QMC_SFL_INDEX_BASE 131072
 int  qmc_add_superfluid_fraction(qmc_ctx *ctx, int setA, int setB, int bins, int *est_index);
 /* realVectorAccumulator state of a superfluidFraction estimator since the last qmc_clear_estimators: sums[bins],

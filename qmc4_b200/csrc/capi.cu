@@ -158,6 +158,11 @@ struct qmc_ctx {
   double *sfl_rec = nullptr;        // [fw_link_depth][cap][3*nSpecies]
   double *sfl_partial = nullptr;    // [chunks][record_steps]
   bool genealogy() const { return !fw_est.empty() || !sfl_est.empty(); }
+  // migration of the records with their walker (qmc_rebalance): slots used per ring level, message scratch
+  int *fw_level_slots = nullptr;    // [fw_link_depth] physical slots the records of that event occupy
+  int *fw_chain = nullptr;
+  double *fw_msg_send = nullptr, *fw_msg_recv = nullptr;
+  size_t fw_chain_bytes = 0, fw_msg_bytes = 0;
   // forceEnergy (energy.cpp:37-61) for the methods without branching (main.cpp:318-335,395-408): a cold pass per sampling step
   bool force_energy = false;
   int64_t n_host = 0;               // population known to the host: constant while branching is off
@@ -770,7 +775,7 @@ int fw_after_step(qmc_ctx *c, int sample)
   const int g = std::max(1, std::min(c->sms * 4, (cap + 255) / 256));
   if (!sample)
     { /* between sampling events the ancestor map is composed with every step's parent map */
-      CK(launch_fw_compose(c->stream, g, c->parent, c->fw_comp[c->fw_comp_cur], c->fw_comp[c->fw_comp_cur ^ 1], c->ctl, 0));
+      CK(launch_fw_compose(c->stream, g, c->parent, c->fw_comp[c->fw_comp_cur], c->fw_comp[c->fw_comp_cur ^ 1], c->ctl, 0, nullptr));
       c->fw_comp_cur ^= 1;
       c->launches += 1;
       return 0;
@@ -810,7 +815,7 @@ int fw_after_step(qmc_ctx *c, int sample)
                               f.sums, f.weight));
       c->launches += 3;
     }
-  CK(launch_fw_compose(c->stream, g, c->parent, nullptr, c->fw_comp[c->fw_comp_cur], c->ctl, 1));
+  CK(launch_fw_compose(c->stream, g, c->parent, nullptr, c->fw_comp[c->fw_comp_cur], c->ctl, 1, c->fw_level_slots + (e % DL)));
   c->launches += 1;
   c->fw_event = e + 1;
   return 0;
@@ -1062,6 +1067,10 @@ void qmc_destroy(qmc_ctx *c)
       cudaFree(f.sums);
       cudaFree(f.weight);
     }
+  cudaFree(c->fw_level_slots);
+  cudaFree(c->fw_chain);
+  cudaFree(c->fw_msg_send);
+  cudaFree(c->fw_msg_recv);
   cudaFree(c->fe_R);
   cudaFree(c->fe_F);
   cudaFree(c->fe_V);
@@ -1218,8 +1227,6 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
 {
   if (!c) return 1;
   if (c->planned) return fail(c, "qmc_set_dmc called twice");
-  if (c->genealogy() && c->nranks > 1)
-    return fail(c, "forward walking and superfluidFraction run on one GPU in this build: walker records do not migrate between ranks yet");
   if (c->genealogy() || c->force_energy) c->pipeline = 1;
   if (c->force_energy && branching_on)
     /* main.cpp attaches the forceEnergy estimator to vmcDriver (:318-335) and to dmcDriver only for svmc (:395-408) */
@@ -1312,6 +1319,8 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
       CK(cudaMalloc(&c->fw_links, (size_t)c->fw_link_depth * capacity * 4));
       CK(cudaMalloc(&c->fw_comp[0], capacity * 4));
       CK(cudaMalloc(&c->fw_comp[1], capacity * 4));
+      CK(cudaMalloc(&c->fw_level_slots, (size_t)c->fw_link_depth * 4));
+      CK(cudaMemset(c->fw_level_slots, 0, (size_t)c->fw_link_depth * 4));
     }
   if (!c->sfl_est.empty())
     {
@@ -1671,8 +1680,20 @@ int qmc_get_estimator(qmc_ctx *c, int est_index, double *sums, int bins, double 
       if (bins != c->plan.est[f.target].bins) return fail(c, "bins mismatch");
       cudaSetDevice(c->device);
       double w = 0;
-      CK(cudaMemcpyAsync(sums, f.sums, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaMemcpyAsync(&w, f.weight, 8, cudaMemcpyDeviceToHost, c->stream));
+      if (c->nranks > 1)
+        { /* estimator::accumulateMPI: sums and weight reduced over the ranks */
+          if (ensure_scratch(c, (size_t)(bins + 1) * 8, 0)) return 1;
+          CK(cudaMemcpyAsync(c->scr, f.sums, (size_t)bins * 8, cudaMemcpyDeviceToDevice, c->stream));
+          CK(cudaMemcpyAsync(c->scr + bins, f.weight, 8, cudaMemcpyDeviceToDevice, c->stream));
+          NK(g_nccl.AllReduce(c->scr, c->scr, (size_t)bins + 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+          CK(cudaMemcpyAsync(sums, c->scr, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+          CK(cudaMemcpyAsync(&w, c->scr + bins, 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+      else
+        {
+          CK(cudaMemcpyAsync(sums, f.sums, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+          CK(cudaMemcpyAsync(&w, f.weight, 8, cudaMemcpyDeviceToHost, c->stream));
+        }
       CK(cudaStreamSynchronize(c->stream));
       if (weight) *weight = w;
       return 0;
@@ -1739,8 +1760,20 @@ int qmc_get_vector_estimator(qmc_ctx *c, int est_index, double *sums, double *we
   const auto &f = c->sfl_est[k];
   if (bins != f.bins || !sums || !weights) return fail(c, "bins mismatch");
   cudaSetDevice(c->device);
-  CK(cudaMemcpyAsync(sums, f.sums, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(weights, f.weights, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (c->nranks > 1)
+    {
+      if (ensure_scratch(c, (size_t)bins * 16, 0)) return 1;
+      CK(cudaMemcpyAsync(c->scr, f.sums, (size_t)bins * 8, cudaMemcpyDeviceToDevice, c->stream));
+      CK(cudaMemcpyAsync(c->scr + bins, f.weights, (size_t)bins * 8, cudaMemcpyDeviceToDevice, c->stream));
+      NK(g_nccl.AllReduce(c->scr, c->scr, (size_t)bins * 2, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+      CK(cudaMemcpyAsync(sums, c->scr, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(weights, c->scr + bins, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+  else
+    {
+      CK(cudaMemcpyAsync(sums, f.sums, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(weights, f.weights, (size_t)bins * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1832,6 +1865,82 @@ int qmc_plan_rebalance(const int *populations, int nRanks, int *sources, int *am
   return 0;
 }
 
+namespace {
+// The genealogical records travel with the walker, as the reference's walker messages carry its storage rings
+// (walkers.cpp:181-233, ptools.cpp:271-401).  Sender: follow the tail walkers' ancestor links through the event ring and
+// pack the records of their lineage; receiver: give every arriving walker a private lineage — slot base+k at EVERY level,
+// base = the largest slot count of any live level, linked to itself — so that later hops find exactly those records.
+int migrate_records(qmc_ctx *c, const std::vector<int> &src, const std::vector<int> &amt, int n_send, int n_recv, int n_cur)
+{
+  const int cap = (int)c->cap, DL = c->fw_link_depth, D = c->fw_depth, stride = c->plan.hist_stride;
+  const int width = c->sfl_est.empty() ? 0 : 3 * c->plan.nSpecies;
+  const long e_last = c->fw_event - 1;
+  const int levels = (int)std::min<long>(c->fw_event, DL);
+  const int row_levels = c->fw_est.empty() ? 0 : (int)std::min<long>(c->fw_event, D);
+  const size_t msz = (size_t)row_levels * stride + (size_t)levels * width;
+  const int comp = c->fw_comp_cur;
+  const size_t need_msg = (size_t)std::max(n_send, n_recv) * msz * 8, need_chain = (size_t)std::max(n_send, 1) * levels * 4;
+  if (need_msg > c->fw_msg_bytes)
+    {
+      cudaFree(c->fw_msg_send);
+      cudaFree(c->fw_msg_recv);
+      c->fw_msg_send = c->fw_msg_recv = nullptr;
+      if (cudaMalloc(&c->fw_msg_send, need_msg) != cudaSuccess || cudaMalloc(&c->fw_msg_recv, need_msg) != cudaSuccess)
+        return fail(c, "rebalance: cannot allocate " + std::to_string(need_msg >> 20) + " MiB for the records of the migrating walkers");
+      c->fw_msg_bytes = need_msg;
+    }
+  if (need_chain > c->fw_chain_bytes)
+    {
+      cudaFree(c->fw_chain);
+      c->fw_chain = nullptr;
+      CK(cudaMalloc(&c->fw_chain, need_chain));
+      c->fw_chain_bytes = need_chain;
+    }
+  if (n_send > 0)
+    {
+      CK(launch_fw_chain(c->stream, c->fw_comp[comp], c->fw_links, DL, cap, e_last, levels, n_cur - n_send, n_send, c->fw_chain));
+      CK(launch_fw_records(c->stream, 0, c->fw_rows, D, row_levels, stride, c->sfl_rec, width, c->fw_links, DL, levels, cap, e_last,
+                           c->fw_chain, 0, c->fw_comp[comp], 0, n_send, c->fw_msg_send));
+      c->launches += 2;
+    }
+  if (msz > 0)
+    {
+      NK(g_nccl.GroupStart());
+      size_t off = 0;
+      for (int r = 0; r < c->nranks; ++r)
+        if (amt[r] > 0 && src[r] == c->rank)
+          {
+            NK(g_nccl.Send(c->fw_msg_send + off, (size_t)amt[r] * msz, NCCL_FLOAT64, r, c->comm, c->stream));
+            off += (size_t)amt[r] * msz;
+          }
+      if (n_recv > 0) NK(g_nccl.Recv(c->fw_msg_recv, (size_t)n_recv * msz, NCCL_FLOAT64, src[c->rank], c->comm, c->stream));
+      NK(g_nccl.GroupEnd());
+    }
+  if (n_recv > 0)
+    {
+      std::vector<int> slots(DL);
+      CK(cudaMemcpyAsync(slots.data(), c->fw_level_slots, (size_t)DL * 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      int base = 0;
+      for (int l = 0; l < levels; ++l) base = std::max(base, slots[(e_last - l) % DL]);
+      if (base + n_recv > cap)
+        return fail(c, "rebalance: no free record slots for the arriving walkers' lineages (capacity " + std::to_string(cap) +
+                           "): raise the capacity passed to qmc_set_dmc");
+      /* arriving walkers are appended at population indices [n_cur - n_send, ...) */
+      CK(launch_fw_records(c->stream, 1, c->fw_rows, D, row_levels, stride, c->sfl_rec, width, c->fw_links, DL, levels, cap, e_last, nullptr,
+                           base, c->fw_comp[comp], n_cur - n_send, n_recv, c->fw_msg_recv));
+      c->launches += 1;
+      const int top = base + n_recv;
+      for (int l = 0; l < levels; ++l)
+        CK(cudaMemcpyAsync(c->fw_level_slots + (e_last - l) % DL, &top, 4, cudaMemcpyHostToDevice, c->stream));
+      for (int l = 0; l < row_levels; ++l)      /* the column sums run over every slot of the level */
+        CK(cudaMemcpyAsync(c->fw_nslots + (e_last - l) % D, &top, 4, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+  return 0;
+}
+} // namespace
+
 int qmc_rebalance(qmc_ctx *c, int64_t *moved)
 {
   if (!c) return 1;
@@ -1880,6 +1989,7 @@ int qmc_rebalance(qmc_ctx *c, int64_t *moved)
     if (n_recv > 0) NK(g_nccl.Recv(c->slab_recv, (size_t)n_recv * wsz, NCCL_FLOAT64, src[c->rank], c->comm, c->stream));
   }
   NK(g_nccl.GroupEnd());
+  if (c->genealogy() && c->fw_event > 0 && migrate_records(c, src, amt, n_send, n_recv, n_cur)) return 1;
   n_cur -= n_send;
   if (n_recv > 0)
     { // received walkers land in free physical slots [n_prev, n_prev+n_recv) and are appended to the population

@@ -113,7 +113,13 @@ cudaError_t configure_kernels_fw(int max_smem_optin);
 int fw_chunks();
 cudaError_t launch_fw_record(cudaStream_t st, int grid, size_t group_bytes, const Plan &plan, const WalkerBuf &buf, const int *n_desc,
                              const Ctl *ctl, double *rows, int *nslots_out);
-cudaError_t launch_fw_compose(cudaStream_t st, int grid, const int *parent, const int *comp_in, int *comp_out, const Ctl *ctl, int fresh);
+cudaError_t launch_fw_compose(cudaStream_t st, int grid, const int *parent, const int *comp_in, int *comp_out, const Ctl *ctl, int fresh,
+                              int *level_slots);
+cudaError_t launch_fw_chain(cudaStream_t st, const int *comp, const int *links, int depth, int cap, long e_last, int levels, int first, int count,
+                            int *chain);
+cudaError_t launch_fw_records(cudaStream_t st, int unpack, double *rows, int row_depth, int row_levels, int stride, double *rec, int width,
+                              int *links, int depth, int levels, int cap, long e_last, const int *chain, int base, int *comp, int first,
+                              int count, double *msg);
 cudaError_t launch_fw_copy_links(cudaStream_t st, int grid, const int *comp, int *link, const Ctl *ctl);
 cudaError_t launch_fw_accumulate(cudaStream_t st, int grid, const int *parent, const int *links, int depth, int cap, long event, int fw,
                                  const Ctl *ctl, int *cnt, const double *rows, const int *nslots, int stride, int offset, int bins,

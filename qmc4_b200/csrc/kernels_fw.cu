@@ -59,11 +59,59 @@ fw_record_kernel(const __grid_constant__ Plan plan, const WalkerBuf buf, const i
 }
 
 // comp maps a walker index of the step about to run to its ancestor slot at the latest sampling event
-__global__ void fw_compose_kernel(const int *parent, const int *comp_in, int *comp_out, const Ctl *ctl, int fresh)
+__global__ void fw_compose_kernel(const int *parent, const int *comp_in, int *comp_out, const Ctl *ctl, int fresh, int *level_slots)
 {
   const int n = ctl->n_cur;
+  if (level_slots && blockIdx.x == 0 && threadIdx.x == 0) *level_slots = ctl->n_prev;   /* slots this event's records occupy */
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     comp_out[i] = fresh ? parent[i] : comp_in[parent[i]];
+}
+
+__global__ void fw_chain_kernel(const int *comp, const int *links, int depth, int cap, long e_last, int levels, int first, int count, int *chain)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  int a = comp[first + k];
+  for (int l = 0; l < levels; ++l)
+    {
+      chain[(size_t)k * levels + l] = a;
+      if (l + 1 < levels) a = links[(size_t)((e_last - l) % depth) * cap + a];
+    }
+}
+
+__global__ void fw_records_kernel(int unpack, double *rows, int row_depth, int row_levels, int stride, double *rec, int width, int *links,
+                                  int depth, int levels, int cap, long e_last, const int *chain, int base, int *comp, int first, int count,
+                                  double *msg)
+{
+  const int k = blockIdx.x;
+  if (k >= count) return;
+  const size_t msz = (size_t)row_levels * stride + (size_t)(rec ? levels : 0) * width;
+  double *m = msg + (size_t)k * msz;
+  for (int l = 0; l < row_levels; ++l)
+    {
+      const int slot = unpack ? base + k : chain[(size_t)k * levels + l];
+      double *row = rows + ((size_t)((e_last - l) % row_depth) * cap + slot) * stride;
+      for (int b = threadIdx.x; b < stride; b += blockDim.x)
+        {
+          if (unpack) row[b] = m[(size_t)l * stride + b];
+          else m[(size_t)l * stride + b] = row[b];
+        }
+    }
+  if (rec)
+    for (int t = threadIdx.x; t < levels * width; t += blockDim.x)
+      {
+        const int l = t / width, w = t % width;
+        const int slot = unpack ? base + k : chain[(size_t)k * levels + l];
+        double *r = rec + ((size_t)((e_last - l) % depth) * cap + slot) * width + w;
+        double *q = m + (size_t)row_levels * stride + t;
+        if (unpack) *r = *q;
+        else *q = *r;
+      }
+  if (unpack)
+    {
+      for (int l = threadIdx.x; l < levels; l += blockDim.x) links[(size_t)((e_last - l) % depth) * cap + base + k] = base + k;
+      if (threadIdx.x == 0) comp[first + k] = base + k;
+    }
 }
 
 __global__ void fw_copy_links_kernel(const int *comp, int *link, const Ctl *ctl)
@@ -220,9 +268,31 @@ cudaError_t launch_fw_record(cudaStream_t st, int grid, size_t group_bytes, cons
   return cudaGetLastError();
 }
 
-cudaError_t launch_fw_compose(cudaStream_t st, int grid, const int *parent, const int *comp_in, int *comp_out, const Ctl *ctl, int fresh)
+cudaError_t launch_fw_compose(cudaStream_t st, int grid, const int *parent, const int *comp_in, int *comp_out, const Ctl *ctl, int fresh,
+                              int *level_slots)
 {
-  QMC_LAUNCH(fw_compose_kernel, grid, 256, 0, st, parent, comp_in, comp_out, ctl, fresh);
+  QMC_LAUNCH(fw_compose_kernel, grid, 256, 0, st, parent, comp_in, comp_out, ctl, fresh, level_slots);
+  return cudaGetLastError();
+}
+
+// ---- migration of the genealogical records with their walker (qmc_rebalance; the reference ships the walker's whole
+// ring, walkers.cpp:181-233 pack/unpack + ptools.cpp:271-401) ---------------------------------------------------------
+// sender: chain[k][l] = slot, at event e_last - l, of the ancestor of the k-th tail walker (population index first + k)
+cudaError_t launch_fw_chain(cudaStream_t st, const int *comp, const int *links, int depth, int cap, long e_last, int levels, int first, int count,
+                            int *chain)
+{
+  QMC_LAUNCH(fw_chain_kernel, (count + 127) / 128, 128, 0, st, comp, links, depth, cap, e_last, levels, first, count, chain);
+  return cudaGetLastError();
+}
+// sender: msg[k] = { rows of the last row_levels events, centre-of-mass records of the last `levels` events } along the chain;
+// receiver (unpack = 1): the same message written to slot base + k of every level, links[level][base + k] = base + k,
+// comp[first + k] = base + k
+cudaError_t launch_fw_records(cudaStream_t st, int unpack, double *rows, int row_depth, int row_levels, int stride, double *rec, int width,
+                              int *links, int depth, int levels, int cap, long e_last, const int *chain, int base, int *comp, int first,
+                              int count, double *msg)
+{
+  QMC_LAUNCH(fw_records_kernel, count, 128, 0, st, unpack, rows, row_depth, row_levels, stride, rec, width, links, depth, levels, cap, e_last,
+             chain, base, comp, first, count, msg);
   return cudaGetLastError();
 }
 

@@ -78,6 +78,19 @@ def test_multirank_steps_and_rebalance_on_emulated_ranks(emu_lib, nranks, N, wpr
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("nranks,sample_every,mid", [(2, 1, 0), (4, 2, 0), (3, 3, 1)])
+def test_forward_walking_records_migrate_between_emulated_ranks(emu_lib, nranks, sample_every, mid):
+    """forward walking + superfluidFraction on several ranks: qmc_rebalance ships the lineage records of the tail walkers
+    (chain of ancestor slots -> message -> private lineage on the receiver); the rank-reduced estimators must equal the
+    oracle's per-walker rings over the GLOBAL genealogy rebuilt from the ranks' traces.  mid = 1: rebalances also happen
+    between two sampling events, where the composed ancestor map (not the fresh parent map) is what travels"""
+    env = _env(emu_lib)
+    env["QMC4_NCCL_LIB"] = os.path.join(EMU_DIR, "libnccl_emu.so")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "multirank_fw_driver.py"), str(nranks), str(sample_every), str(mid)],
+                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.skipif(os.environ.get("QMC4_TEST_EMULATED_SLOW") != "1", reason="minutes of CPU: set QMC4_TEST_EMULATED_SLOW=1")
 def test_experimental_pipeline2_bitwise_on_emulated_kernels(emu_lib):
     env = _env(emu_lib)

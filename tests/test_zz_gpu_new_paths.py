@@ -164,6 +164,20 @@ def test_superfluid_fraction_measurement_file(tmp_path):
     assert np.all(np.abs(W[1:] / free[1:] - 1) < 0.35), (W, free)
 
 
+def test_forward_walking_records_migrate_between_two_gpus():
+    """the multi-rank record migration of qmc_rebalance on real GPUs + NCCL (tests/emu/multirank_fw_driver.py, one host
+    thread per GPU): needs 2 GPUs, skipped on the 1-GPU box; its logic runs on emulated ranks in the CPU suite"""
+    import subprocess
+    import sys
+    import torch
+    if hd.BIN.endswith("_emu") or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "emu", "multirank_fw_driver.py"), "2", "1"],
+                       env=dict(os.environ, QMC4_FW_DRIVER_REAL_GPUS="1"), cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_forward_walking_errors():
     cfg = cases.structure_factor()
     cfg["measurements"][0].update(recordSteps=4, forwardWalkingSteps=[1])
