@@ -451,7 +451,8 @@ def test_host_driver_force_energy_file(tmp_path):
     """forceEnergy.dat: header always (main.cpp:273 constructs the estimator unconditionally), one %.12e average per block
     for svmc with a {"kind": "forceEnergy"} measurement, header only for dmc.  Under |psi|^2 sampling <forceEnergy> =
     <E_L> (integration by parts), so for the harmonic trap both sit near the variational energy."""
-    cfg = dict(cases.vmc_case(), walkers=16, stepsPerBlock=20, nBlocks=4, correlationSteps=1)
+    emu = hd.BIN.endswith("_emu")                 # the thread emulation is ~1e4 x slower: fewer chains, looser statistics
+    cfg = dict(cases.vmc_case(), walkers=10 if emu else 512, stepsPerBlock=8 if emu else 200, nBlocks=4, correlationSteps=1)
     cfg["measurements"] = cfg["measurements"] + [{"kind": "forceEnergy", "label": "forceEnergy"}]
     p = hd.run(cfg, str(tmp_path))
     assert p.returncode == 0, p.stderr
@@ -460,7 +461,7 @@ def test_host_driver_force_energy_file(tmp_path):
     fe = np.array([float(x) for x in lines[1:] if x.strip()])
     e = np.loadtxt(tmp_path / "energy.dat", skiprows=1)
     assert len(fe) == 4 and len(e) == 4 and np.isfinite(fe).all()
-    assert abs(fe.mean() - e.mean()) < 0.25 * abs(e.mean())
+    assert abs(fe[1:].mean() - e[1:].mean()) < (0.4 if emu else 0.05) * abs(e[1:].mean())
     os.remove(tmp_path / "forceEnergy.dat")
     p = hd.run(dict(cfg, method="dmc", walkers=16, timeStep=1e-3, stepsPerBlock=3, nBlocks=2), str(tmp_path))
     assert p.returncode == 0, p.stderr
