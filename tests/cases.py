@@ -160,6 +160,16 @@ def dmc_cases():
     return {"trap_N10": t, "pbc_N16": p}
 
 
+def dmc_pure_estimators_case():
+    """Full DMC run for statistical parity (2) of the pure-estimator family against the reference's CPU run: forward-walking g(r)
+    (ring of 12 records, 0 and 8 steps forward) and the superfluid-fraction winding estimator (12 lags)."""
+    p = pbc(16, 2.6, walkers=400, meas=[
+        {"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": 13, "minx": 0, "maxx": 1.3, "recordSteps": 12, "forwardWalkingSteps": [0, 8]},
+        {"kind": "superfluidFraction", "label": "rho", "sets": [0, 0], "bins": 12}])
+    p.update(timeStep=5e-3, stepsPerBlock=100, nBlocks=140, seed=79, correlationSteps=3)
+    return p
+
+
 def vmc_case():
     """method "vmc" (vmcDriver.cpp): the trap of config 1 sampled from |psi|^2; the reference runs one chain"""
     t = trap(10)

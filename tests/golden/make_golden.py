@@ -51,8 +51,37 @@ def force_energy(ref):
     np.savez_compressed(os.path.join(HERE, "force_energy.npz"), **out)
 
 
+def parse_blocks(path):
+    """per-block value columns of a histogram/vector estimator file (header line, blocks separated by blank lines)"""
+    txt = open(path).read()
+    txt = txt[txt.index("\n") + 1:]
+    out = []
+    for blk in txt.split("\n\n"):
+        rows = [r.split() for r in blk.strip().split("\n") if r.strip()]
+        if rows:
+            out.append([float(r[1]) for r in rows])
+    return out
+
+
+def dmc_pure(ref):
+    """the reference's own binary on cases.dmc_pure_estimators_case() -> dmc_reference_pure_run.json (about a minute)"""
+    cfg = cases.dmc_pure_estimators_case()
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, "input.json"), "w") as f:
+            json.dump(cfg, f)
+        subprocess.check_call([REF_BIN, "input.json"], cwd=tmp, stdout=subprocess.DEVNULL)
+        entry = {"input": cfg, "energy_per_block": np.loadtxt(os.path.join(tmp, "energy.dat"), skiprows=1).tolist()}
+        for name in ("pair_fw0", "pair_fw8", "rho"):
+            entry[name + "_per_block"] = parse_blocks(os.path.join(tmp, name + ".dat"))
+    with open(os.path.join(HERE, "dmc_reference_pure_run.json"), "w") as f:
+        json.dump(entry, f)
+
+
 def main():
     ref = Ref()
+    if "--dmc-pure" in sys.argv:
+        dmc_pure(ref)
+        return
     if "--superfluid" in sys.argv or "--force-energy" in sys.argv:
         if "--superfluid" in sys.argv:
             superfluid(ref)
@@ -155,6 +184,8 @@ def main():
                 res[name] = entry
         with open(os.path.join(HERE, "dmc_reference_runs.json"), "w") as f:
             json.dump(res, f)
+    if "--dmc" in sys.argv:
+        dmc_pure(ref)
     if "--vmc" in sys.argv or "--dmc" in sys.argv:
         cfg = cases.vmc_case()
         with tempfile.TemporaryDirectory() as tmp:

@@ -178,6 +178,40 @@ def test_forward_walking_records_migrate_between_two_gpus():
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-2000:]
 
 
+@pytest.mark.skipif(hd.BIN.endswith("_emu"), reason="5.6e6 walker-moves: hardware only")
+def test_pure_estimators_statistical_parity_with_reference_run(tmp_path):
+    """parity (2) for the pure-estimator family: forward-walking g(r) (0 and 8 sampling steps forward) and the superfluid-
+    fraction winding estimator of a full DMC run against the reference's own CPU run of the same input
+    (tests/golden/dmc_reference_pure_run.json, make_golden.py --dmc-pure), bin by bin within 2 sigma of the blocked errors"""
+    import json
+    fx = json.load(open(os.path.join(hd.GOLD, "dmc_reference_pure_run.json")))
+    cfg = fx["input"]
+    p = hd.run(cfg, str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    skip = 20                                             # equilibration blocks
+
+    def blocks(name):
+        txt = open(tmp_path / (name + ".dat")).read()
+        txt = txt[txt.index("\n") + 1:]
+        out = [[float(r.split()[1]) for r in b.strip().split("\n") if r.strip()] for b in txt.split("\n\n")]
+        return np.array([o for o in out if o])
+
+    e = np.loadtxt(tmp_path / "energy.dat", skiprows=1)[skip:]
+    e_ref = np.asarray(fx["energy_per_block"])[skip:]
+    assert abs(e.mean() - e_ref.mean()) < 2.5 * np.hypot(hd._blocked_error(e), hd._blocked_error(e_ref))
+    for name in ("pair_fw0", "pair_fw8", "rho"):
+        got, ref = blocks(name), np.asarray(fx[name + "_per_block"])
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        got, ref = got[skip:], ref[skip:]
+        cols = [i for i in range(ref.shape[1]) if ref[:, i].std() > 0]          # lag 0 of rho is identically 0
+        sg = np.hypot([hd._blocked_error(got[:, i]) for i in cols], [hd._blocked_error(ref[:, i]) for i in cols])
+        z = np.abs(got[:, cols].mean(0) - ref[:, cols].mean(0)) / np.maximum(sg, 1e-12)
+        assert (z < 2).mean() > 0.7 and z.max() < 4.5, (name, z)
+    rho = blocks("rho")[skip:].mean(0)
+    free = 3 * cfg["N"][0] * cfg["timeStep"] * (cfg["correlationSteps"] + 1) * np.arange(len(rho))
+    assert np.all(np.abs(rho[1:] / free[1:] - 1) < 0.1)                         # superfluid fraction ~ acceptance ~ 0.96
+
+
 def test_forward_walking_errors():
     cfg = cases.structure_factor()
     cfg["measurements"][0].update(recordSteps=4, forwardWalkingSteps=[1])
