@@ -35,6 +35,23 @@ except Exception as e:
 EOF
 done
 
+step "3b. launch-geometry sweep of the default pipeline at config 2 (warps per walker, resident CTAs per SM)"
+for knob in "QMC4_WPW=1" "QMC4_WPW=2" "QMC4_WPW=4" "QMC4_CTAS_PER_SM=1" "QMC4_CTAS_PER_SM=2"; do
+  env $knob timeout 300 python bench.py --steps 100 --no-cpu-baseline > $OUT/bench_cfg2_${knob/=/_}.json 2> $OUT/bench_cfg2_${knob/=/_}.err
+  python - <<EOF2 | tee -a $OUT/session.log
+import json
+try:
+    d = json.loads(open("$OUT/bench_cfg2_${knob/=/_}.json").read().strip().splitlines()[-1])
+    print("$knob: %.4g walker-moves/s, %.4f ms/step, roofline %.3f, kernel %s" % (d["value"], d["ms_per_step"], d["roofline"]["frac"], d["kernel"]))
+except Exception as e:
+    print("$knob: no result (%s)" % e)
+EOF2
+done
+
+step "3c. new statistical parity test of the pure estimators alone (kept out of -x's way above)"
+timeout 600 python -m pytest tests/test_zz_gpu_new_paths.py -m gpu -q -p no:cacheprovider -k "pure_estimators or force_energy or superfluid or dipolar" > $OUT/pytest_r1b.log 2>&1
+tail -5 $OUT/pytest_r1b.log | tee -a $OUT/session.log
+
 step "4. the other BASELINE shapes (1 GPU)"
 for cfg in 5 3 4 1; do
   timeout 900 python bench.py --config $cfg --steps 20 --no-cpu-baseline > $OUT/bench_cfg${cfg}.json 2> $OUT/bench_cfg${cfg}.err

@@ -100,6 +100,58 @@ def test_experimental_pipeline2_bitwise_on_emulated_kernels(emu_lib):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def _tsan_inputs():
+    """small host-driver inputs that together reach every kernel family"""
+    import copy
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    small = dict(stepsPerBlock=3, nBlocks=2, correlationSteps=0)
+    fw = cases.forward_walking_cases()
+    pair = copy.deepcopy(fw["pbc_pair"])
+    pair["measurements"].append({"kind": "superfluidFraction", "label": "rho", "sets": [0, 0], "bins": 4})
+    vmc = copy.deepcopy(cases.vmc_case())
+    vmc["measurements"].append({"kind": "forceEnergy", "label": "forceEnergy"})
+    out = {
+        "fw_pair_superfluid": dict(pair, walkers=10, delta_walkers=2, stepsPerBlock=3, nBlocks=2, correlationSteps=1),
+        "fw_trimer": dict(fw["three_body_trimer"], walkers=8, delta_walkers=2, **small),
+        "fw_mixture": dict(fw["mixture_g01"], walkers=8, delta_walkers=2, stepsPerBlock=4, nBlocks=2, correlationSteps=0),
+        "fw_impurity_scalar": dict(fw["impurity_hyper"], walkers=8, delta_walkers=2, **small),
+        "triplets_dis": dict(cases.mixture3(), walkers=6, delta_walkers=2, timeStep=1e-3, **small),
+        "triplets_dis_hard_sphere": dict(cases.mixture3(hs=1.3), walkers=6, delta_walkers=2, timeStep=1e-3, **small),
+        "vmc_force_energy": dict(vmc, walkers=6, stepsPerBlock=3, nBlocks=2, correlationSteps=1),
+        "generic_dipolar_rep": dict(cases.pbc(10, 5.2, walkers=6, jastrow=cases.DIPOLAR_REP), delta_walkers=2, timeStep=1e-3, **small),
+        "structure_factor": dict(cases.structure_factor(), walkers=6, delta_walkers=2, **small),
+    }
+    return out
+
+
+@pytest.mark.skipif(os.environ.get("QMC4_TEST_EMULATED_TSAN") != "1", reason="~10 minutes of CPU: set QMC4_TEST_EMULATED_TSAN=1")
+def test_kernels_are_race_free_under_thread_sanitizer(tmp_path):
+    """ThreadSanitizer over the emulation (tests/emu/Makefile `tsan`): CUDA threads are OS threads and every barrier, shuffle
+    and atomic is a std::atomic operation, so an access pair the GPU does not order shows up as a data race.  Run for all
+    kernel families through the host driver, on 1 emulated GPU, on 2 (NCCL stand-in, record migration) and with pipeline 2."""
+    import json
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR, "-j4", "tsan"])
+    tsan = os.path.join(EMU_DIR, "tsan")
+
+    def run(name, cfg, *extra, **env):
+        d = tmp_path / name
+        d.mkdir()
+        json.dump(cfg, open(d / "input.json", "w"))
+        e = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0", QMC4_EMU_DEVICES="1",
+                 QMC4_NCCL_LIB=os.path.join(tsan, "libnccl_emu.so"))
+        e.update(env)
+        p = subprocess.run([os.path.join(tsan, "dmc_b200_emu"), "input.json", *extra], cwd=d, env=e, capture_output=True, text=True, timeout=1800)
+        assert p.returncode == 0, name + p.stderr[-1500:]
+        assert "ThreadSanitizer" not in p.stderr, name + "\n" + p.stderr[:3000]
+
+    inputs = _tsan_inputs()
+    for name, cfg in inputs.items():
+        run(name, cfg)
+    run("two_gpus_record_migration", inputs["fw_pair_superfluid"], "--gpus", "2", QMC4_EMU_DEVICES="2")
+    run("pipeline2", inputs["structure_factor"], QMC4_PIPELINE="2")
+
+
 def _run_host(tmp_path, cfg, *extra, devices=1):
     import json
     with open(os.path.join(tmp_path, "input.json"), "w") as f:
