@@ -125,25 +125,28 @@ def _tsan_inputs():
     return out
 
 
-@pytest.mark.skipif(os.environ.get("QMC4_TEST_EMULATED_TSAN") != "1", reason="~10 minutes of CPU: set QMC4_TEST_EMULATED_TSAN=1")
-def test_kernels_are_race_free_under_thread_sanitizer(tmp_path):
-    """ThreadSanitizer over the emulation (tests/emu/Makefile `tsan`): CUDA threads are OS threads and every barrier, shuffle
-    and atomic is a std::atomic operation, so an access pair the GPU does not order shows up as a data race.  Run for all
-    kernel families through the host driver, on 1 emulated GPU, on 2 (NCCL stand-in, record migration) and with pipeline 2."""
+@pytest.mark.skipif(os.environ.get("QMC4_TEST_EMULATED_SANITIZERS") != "1", reason="~15 minutes of CPU: set QMC4_TEST_EMULATED_SANITIZERS=1")
+@pytest.mark.parametrize("san", ["tsan", "asan"])
+def test_kernels_under_sanitizers(tmp_path, san):
+    """ThreadSanitizer / AddressSanitizer over the emulation (tests/emu/Makefile `tsan`, `asan`).  tsan: CUDA threads are OS
+    threads and every barrier, shuffle and atomic is a std::atomic operation, so an access pair the GPU does not order shows up
+    as a data race.  asan: every device allocation and every launch's shared memory is its own heap block, so an out-of-range
+    index is an error.  Run for all kernel families through the host driver, on 1 emulated GPU, on 2 (NCCL stand-in, record
+    migration) and with pipeline 2."""
     import json
-    subprocess.check_call(["make", "-s", "-C", EMU_DIR, "-j4", "tsan"])
-    tsan = os.path.join(EMU_DIR, "tsan")
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR, "-j4", san])
+    d_san = os.path.join(EMU_DIR, san)
 
     def run(name, cfg, *extra, **env):
         d = tmp_path / name
         d.mkdir()
         json.dump(cfg, open(d / "input.json", "w"))
-        e = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0", QMC4_EMU_DEVICES="1",
-                 QMC4_NCCL_LIB=os.path.join(tsan, "libnccl_emu.so"))
+        e = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0", ASAN_OPTIONS="detect_leaks=0", QMC4_EMU_DEVICES="1",
+                 QMC4_NCCL_LIB=os.path.join(d_san, "libnccl_emu.so"))
         e.update(env)
-        p = subprocess.run([os.path.join(tsan, "dmc_b200_emu"), "input.json", *extra], cwd=d, env=e, capture_output=True, text=True, timeout=1800)
+        p = subprocess.run([os.path.join(d_san, "dmc_b200_emu"), "input.json", *extra], cwd=d, env=e, capture_output=True, text=True, timeout=1800)
         assert p.returncode == 0, name + p.stderr[-1500:]
-        assert "ThreadSanitizer" not in p.stderr, name + "\n" + p.stderr[:3000]
+        assert "Sanitizer" not in p.stderr, name + "\n" + p.stderr[:3000]
 
     inputs = _tsan_inputs()
     for name, cfg in inputs.items():
