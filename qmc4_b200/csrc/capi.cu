@@ -2086,6 +2086,17 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "n_triplet_passes") *value = c->plan.n3b;
   else if (k == "n_estimators") *value = c->plan.nest;
   else if (k == "hist_stride") *value = c->plan.hist_stride;
+  else if (k == "global_population")
+    { /* pTools::sum(current_walkers.size()) (dmcDriver.cpp:204): the population entry of the per-step all-reduce */
+      if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
+      cudaSetDevice(c->device);
+      if (c->pipeline == 2 && sync_all(c)) return 1;
+      Ctl h;
+      CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      /* gsum[1] = sum of the ranks' populations after the last step; migration conserves it */
+      *value = c->nranks > 1 ? h.gsum[1] : (double)h.n_cur;
+    }
   else if (k == "fw_events") *value = (double)c->fw_event;
   else if (k == "fw_depth") *value = c->fw_depth;
   else if (k == "fw_link_depth") *value = c->fw_link_depth;

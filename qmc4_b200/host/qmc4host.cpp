@@ -475,7 +475,9 @@ void dmcDriver::out(size_t iBlock)
       if (!vmcMode)
         {
           std::cout << ansiColor("cyan") << "Curr. Walkers: " << ansiColor("default");
-          std::cout << (long)r.population << std::endl;
+          double globalPopulation = r.population;        /* the reference prints the sum over the ranks (dmcDriver.cpp:204,222) */
+          if (nranks > 1) check(qmc_get_info(ctx, "global_population", &globalPopulation));
+          std::cout << (long)globalPopulation << std::endl;
         }
       energyEst->dump();
       for (auto *e : estimators) e->dump();
