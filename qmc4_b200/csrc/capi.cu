@@ -1248,6 +1248,13 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
   D.nranks = c->nranks;
   if (capacity <= 0) capacity = 2 * (targetWalkers + deltaWalkers) / std::max(1, c->nranks) + 64;
   c->cap = capacity;
+  if (c->genealogy())
+    { /* ring depths (host logic): histogram rows for max fw + 1 events, links and centre-of-mass records for max(that, bins) */
+      int maxfw = 0;
+      for (auto &f : c->fw_est) maxfw = std::max(maxfw, f.fw);
+      c->fw_depth = maxfw + 1;
+      c->fw_link_depth = std::max(c->fw_depth, c->sfl_record_steps);
+    }
   if (c->planning_only)
     {
       c->cfg.grid = c->sms * 2;
@@ -1312,10 +1319,6 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
     }
   if (c->genealogy())
     { /* the event clock both record rings share: ancestor links + the composed parent maps between sampling events */
-      int maxfw = 0;
-      for (auto &f : c->fw_est) maxfw = std::max(maxfw, f.fw);
-      c->fw_depth = maxfw + 1;
-      c->fw_link_depth = std::max(c->fw_depth, c->sfl_record_steps);
       CK(cudaMalloc(&c->fw_links, (size_t)c->fw_link_depth * capacity * 4));
       CK(cudaMalloc(&c->fw_comp[0], capacity * 4));
       CK(cudaMalloc(&c->fw_comp[1], capacity * 4));

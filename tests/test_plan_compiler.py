@@ -195,3 +195,44 @@ def test_errors():
         plan(cases.pbc(4000, 20.0))
     with pytest.raises(RuntimeError, match="Jastrow cannot be negative"):       # jastrowSquareWell.cpp:29-33 (the reference exits)
         plan(cases.pbc(8, 5.0, jastrow={"kind": "squareWell", "V0": 2.4674011002723395, "R0": 1.0, "Rm": 1.6, "alpha": 0.5, "aInverse": 0.7, "cut_off": 2.5}))
+
+
+def test_superfluid_force_energy_and_dipolar_rep_are_planned_and_validated_without_a_device():
+    """the round-1 continuation's host logic: measurement wiring, derived dipolar_rep constants, error semantics"""
+    # superfluidFraction: the record ring shares the forward-walking event clock; link depth = max(max fw + 1, bins)
+    s = plan(cases.superfluid_cases()["mixture_rho"])
+    assert s.info("fw_link_depth") == 5 and [e["label"] for e in s.estimators] == ["rho11", "g01", "rho01", "rho00"]
+    assert all(e.get("vector") for e in s.estimators if e["kind"] == "superfluidFraction")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        s.estimator(s.estimators[0]["index"])
+    s.close()
+    fw = cases.forward_walking_cases()["pbc_pair"]
+    fw["measurements"].append({"kind": "superfluidFraction", "label": "rho", "sets": [0, 0], "bins": 3})
+    s = plan(fw)
+    assert s.info("fw_depth") == 4 and s.info("fw_link_depth") == 4       # max fw = 3 -> 4 events of rows and links
+    s.close()
+    bad = cases.superfluid_cases()["mixture_rho"]
+    bad["measurements"][2]["bins"] = 7
+    with pytest.raises(RuntimeError, match="same .bins"):                   # correlationEstimator.cpp:333: record size = data.size()/bins
+        plan(bad)
+    bad = cases.superfluid_cases()["pbc_rho"]
+    bad["measurements"][0]["sets"] = [0, 1]
+    with pytest.raises(RuntimeError, match="set out of range"):
+        plan(bad)
+    with pytest.raises(RuntimeError, match="vmc and superfluid"):           # main.cpp:279-282
+        plan(dict(cases.superfluid_cases()["pbc_rho"], method="vmc"))
+    # forceEnergy: attached for vmc / svmc only (main.cpp:318-335,395-408)
+    cfg = cases.pbc(8, 4.0)
+    cfg["measurements"] = [{"kind": "forceEnergy", "label": "forceEnergy"}]
+    for method, on in (("dmc", False), ("svmc", True), ("vmc", True)):
+        s = plan(dict(cfg, method=method))
+        assert s.force_energy_enabled is on
+        s.close()
+    # dipolar_rep: D = sqrt(j["D"]), lBox = 2 cut_off, k = pi / lBox, logC = log(C) (jastrowDipolar.cpp:3-27); generic kernel
+    s = plan(cases.pbc(10, 5.2, jastrow=cases.DIPOLAR_REP))
+    J = cases.DIPOLAR_REP
+    assert s.info("kernel_variant") == KSEL_GENERIC and s.info("pass0.jkind") == 12
+    got = [s.info("pass0.p%d" % i) for i in range(6)]
+    exp = [math.sqrt(J["D"]), J["cut_off"], J["matching_point"], J["alpha"], math.pi / (2 * J["cut_off"]), math.log(J["C"])]
+    assert got == exp
+    s.close()
