@@ -140,6 +140,27 @@ def test_superfluid_fraction_without_branching_and_errors(port):
         System.from_input(bad)
 
 
+def test_pure_estimators_are_bitwise_reproducible():
+    """fixed-order reductions everywhere (column sums over slot chunks, CTA tree + chunk order for the winding products):
+    two runs of the same input give identical bits, the property DESIGN.md §3 claims for the physics path"""
+    import copy
+    cfg = copy.deepcopy(cases.forward_walking_cases()["pbc_pair"])
+    cfg["measurements"].append({"kind": "superfluidFraction", "label": "rho", "sets": [0, 0], "bins": 4})
+    L = np.asarray(cfg["lBox"])
+    R = (np.random.default_rng(4).uniform(-0.5, 0.5, size=(cfg["walkers"], 3, cfg["N"][0])) * L[None, :, None]).reshape(cfg["walkers"], -1)
+    runs = []
+    for _ in range(2):
+        s = System.from_input(cfg)
+        s.upload(R)
+        s.step(14, 2)
+        runs.append({e["label"]: s.estimator(e["index"]) for e in s.estimators})
+        s.close()
+    for label in runs[0]:
+        (a, wa), (b, wb) = runs[0][label], runs[1][label]
+        assert np.array_equal(a, b) and np.array_equal(wa, wb), label
+        assert np.asarray(wa).sum() > 0
+
+
 def test_superfluid_fraction_measurement_file(tmp_path):
     """<label>.dat of the host driver (superfluidFractionEstimator::write, correlationEstimator.cpp:305-320): header
     "x <label>", per block the rows "lag average" of the lags that received data.  Physics check: the pair Jastrow's
