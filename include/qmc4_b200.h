@@ -244,7 +244,10 @@ int  qmc_synchronize(qmc_ctx *ctx);
 int  qmc_comm_unique_id(void *uniqueId128);
 int  qmc_comm_init(qmc_ctx *ctx, const void *uniqueId128, int rank, int nranks);
 /* walkerDistribution::isendReceive + wait (ptools.cpp:271-401): allgather populations, alias-method
- * plan, ship tail walkers to under-full ranks.  moved = walkers sent (+) / received (-). */
+ * plan, ship tail walkers to under-full ranks.  moved = walkers sent (+) / received (-).
+ * With forward walking / superfluidFraction the walkers' records travel too (the reference's walker messages carry the
+ * storage rings, walkers.cpp:181-233): per walker (max fw + 1) x bins + bins_sfl x 3 nSpecies doubles; the receiver needs
+ * free record slots above the largest population of the last `depth` sampling events (error if the capacity is too small). */
 int  qmc_rebalance(qmc_ctx *ctx, int64_t *moved);
 /* The planner alone (ptools.cpp:93-161), host-side, for tests. */
 int  qmc_plan_rebalance(const int *populations, int nRanks, int *sources, int *amounts);
