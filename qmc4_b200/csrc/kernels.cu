@@ -421,7 +421,8 @@ __global__ void tabulate_kernel(const RadialFn J, const double *coef, double min
 {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     {
-      const double x = minx + ((double)i + 0.5) * deltax;
+      /* jastrow.h:51 rounds the product before the sum (host code, no contraction): no FMA here */
+      const double x = __dadd_rn(minx, __dmul_rn((double)i + 0.5, deltax));
       double d0, d1, d2;
       eval_radial(J, coef, x, d0, d1, d2);
       out[4 * i + 0] = x;

@@ -123,6 +123,16 @@ static inline double __fma_rz(double a, double b, double c)
   fesetround(old);
   return r;
 }
+static inline double __dmul_rn(double a, double b)
+{
+  volatile double r = a * b;       /* rounded product: the build uses -ffp-contract=off */
+  return r;
+}
+static inline double __dadd_rn(double a, double b)
+{
+  volatile double r = a + b;
+  return r;
+}
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline float emu_log2f(float x) { return log2f(x); }
 static inline void emu_sincosf(float x, float *s, float *c)
