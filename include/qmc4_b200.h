@@ -249,6 +249,13 @@ int  qmc_comm_init(qmc_ctx *ctx, const void *uniqueId128, int rank, int nranks);
  * storage rings, walkers.cpp:181-233): per walker (max fw + 1) x bins + bins_sfl x 3 nSpecies doubles; the receiver needs
  * free record slots above the largest population of the last `depth` sampling events (error if the capacity is too small). */
 int  qmc_rebalance(qmc_ctx *ctx, int64_t *moved);
+/* Inside qmc_step the same migration runs by itself, ONE STEP LATE and overlapped with the next step's moves exactly as
+ * dmcDriver::step does (isend after step k, dmcDriver.cpp:112,150-157; wait after the local loop of step k+1, arrivals
+ * advanced within that step, :133-136): the plan is derived on every rank from the population vector the per-step
+ * all-reduce carries, tail walkers travel on a second stream while the move kernel of the next step runs.
+ * every: plan every `every` steps (default 1, like the reference).  band: dead band — transfers are posted only when
+ * max-min population exceeds band x mean population (default 0.005; 0 = any imbalance, like the reference). */
+int  qmc_set_migration(qmc_ctx *ctx, int every, double band);
 /* The planner alone (ptools.cpp:93-161), host-side, for tests. */
 int  qmc_plan_rebalance(const int *populations, int nRanks, int *sources, int *amounts);
 

@@ -41,7 +41,7 @@ EXPORTS = [
     "qmc_add_potential_term", "qmc_add_estimator", "qmc_set_dmc", "qmc_eval", "qmc_eval_device",
     "qmc_accumulate_configs", "qmc_upload_walkers", "qmc_download_walkers", "qmc_step",
     "qmc_step_traced", "qmc_block_results", "qmc_get_estimator", "qmc_clear_estimators",
-    "qmc_synchronize", "qmc_comm_unique_id", "qmc_comm_init", "qmc_rebalance", "qmc_plan_rebalance",
+    "qmc_synchronize", "qmc_comm_unique_id", "qmc_comm_init", "qmc_rebalance", "qmc_set_migration", "qmc_plan_rebalance",
     "qmc_get_info", "qmc_stream", "qmc_add_forward_walking", "qmc_set_vmc", "qmc_tabulate_wavefunction",
     "qmc_add_superfluid_fraction", "qmc_get_vector_estimator", "qmc_enable_force_energy", "qmc_get_force_energy",
 ]
@@ -91,6 +91,7 @@ def load():
     lib.qmc_comm_unique_id.argtypes = [vp]
     lib.qmc_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.qmc_rebalance.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.qmc_set_migration.argtypes = [vp, C.c_int, C.c_double]
     lib.qmc_plan_rebalance.argtypes = [c_int_p, C.c_int, c_int_p, c_int_p]
     lib.qmc_get_info.argtypes = [vp, C.c_char_p, c_double_p]
     lib.qmc_stream.argtypes = [vp]

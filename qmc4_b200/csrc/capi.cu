@@ -27,6 +27,7 @@ struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_t, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*CommAbort)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -60,6 +61,7 @@ struct NcclApi {
     QMC_SYM(GetUniqueId, "ncclGetUniqueId")
     QMC_SYM(CommInitRank, "ncclCommInitRank")
     QMC_SYM(CommDestroy, "ncclCommDestroy")
+    QMC_SYM(CommAbort, "ncclCommAbort")
     QMC_SYM(AllReduce, "ncclAllReduce")
     QMC_SYM(AllGather, "ncclAllGather")
     QMC_SYM(Send, "ncclSend")
@@ -129,13 +131,22 @@ struct qmc_ctx {
   double prop_ms = 0;
   long prop_launches_timed = 0;
   int time_kernels = 0;
-  // experimental pipeline 2 (QMC4_PIPELINE=2): branching decided in the scan kernel, estimators in their own
-  // kernel, the per-step all-reduce on a second stream off the critical path
-  int pipeline = 1;
+  // pipeline 2 (default; kernels_v2.cu): branching decided in the scan kernel, estimators in their own kernel, the per-step
+  // all-reduce and the walker migration on a second (high-priority) stream off the critical path.  QMC4_PIPELINE=1 selects
+  // the fused pipeline of kernels.cu, which runs with genealogical records, forceEnergy and the traced step also carry.
+  int pipeline = 2;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_scan = nullptr, ev_ar = nullptr;
+  cudaEvent_t ev_scan = nullptr, ev_ar = nullptr, ev_mig = nullptr;
   bool ar_pending = false;
-  int est_occ = 2, est_grid = 0;      // estimator kernel of pipeline 2: resident CTAs per SM it is compiled for, its grid
+  int *flags = nullptr;             // [cap] accepted bit per walker (move kernel -> scan)
+  double *h_sums = nullptr;         // pinned copy of Ctl::gsum after the last all-reduce: what the migration planner reads
+  bool pops_pending = false;        // h_sums holds populations the planner has not looked at yet
+  int mig_every = 1;                // plan a migration every mig_every steps ...
+  double mig_band = 0.005;          // ... if max-min population exceeds this fraction of the mean (dead band), min 1 walker
+  long mig_phase = 0, mig_events = 0, mig_out = 0, mig_in = 0;
+  int slab_walkers = 0;             // walkers one migration slab holds (bounds a step's transfers)
+  unsigned long long *d_checksum = nullptr;
+  int est_occ = 4, est_grid = 0;      // estimator kernel of pipeline 2: resident CTAs per SM it is compiled for, its grid
   double *e_old = nullptr;
   // forward walking (kernels_fw.cu; correlationEstimator.cpp): ring of per-slot histogram rows + ancestor links
   struct FwEst { int target, fw, record_steps; double *sums = nullptr, *weight = nullptr; };
@@ -723,7 +734,7 @@ int allreduce_sums(qmc_ctx *c)
   if (c->nranks > 1)
     {
       /* the next propagate kernel derives E_T from gsum itself: one 80-byte collective per step, no extra launch */
-      NK(g_nccl.AllReduce(c->ctl->lsum, c->ctl->gsum, 2 + MAX_RANKS, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+      NK(g_nccl.AllReduce(c->ctl->lsum, c->ctl->gsum, NSUM, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
     }
   return 0;
 }
@@ -821,25 +832,109 @@ int fw_after_step(qmc_ctx *c, int sample)
   return 0;
 }
 
+// The migration plan of one step, identical on every rank (all inputs come from the all-reduced vector in h_sums):
+// alias-method plan (ptools.cpp:93-161) inside a dead band, clamped to the receivers' free slots and to the slab size.
+void plan_migration(qmc_ctx *c, std::vector<int> &src, std::vector<int> &amt, int &n_send, int &n_recv)
+{
+  const int nr = c->nranks;
+  std::vector<int> pops(nr), fre(nr), sent(nr, 0);
+  src.assign(nr, 0);
+  amt.assign(nr, 0);
+  n_send = n_recv = 0;
+  long total = 0;
+  int mx = 0, mn = 1 << 30;
+  for (int r = 0; r < nr; ++r)
+    {
+      pops[r] = (int)c->h_sums[2 + r];
+      fre[r] = (int)c->h_sums[2 + MAX_RANKS + r];
+      total += pops[r];
+      mx = std::max(mx, pops[r]);
+      mn = std::min(mn, pops[r]);
+    }
+  const double band = std::max(1.0, c->mig_band * (double)total / nr);
+  if ((double)(mx - mn) <= band) return;
+  qmc_plan_rebalance(pops.data(), nr, src.data(), amt.data());
+  for (int r = 0; r < nr; ++r)
+    if (amt[r] > 0)
+      {
+        const int a = std::min(std::min(amt[r], fre[r]), c->slab_walkers - sent[src[r]]);
+        amt[r] = std::max(a, 0);
+        sent[src[r]] += amt[r];
+      }
+  n_send = sent[c->rank];
+  n_recv = amt[c->rank];
+}
+
 int one_step_v2(qmc_ctx *c, int accumulate)
-{ /* propagate(k) || all-reduce(k-1)  ->  scan(k)  ->  { all-reduce(k) on the comm stream } || estimators(k) || propagate(k+1) */
+{ /* move(k) || { all-reduce(k-1), migration(k-1) }  ->  [move(k) on the arrivals]  ->  scan(k)  ->  { all-reduce(k) } || estimators(k) || move(k+1) */
   StepArgs a = make_step_args(c, accumulate);
   a.hist = nullptr;
+  a.flags = c->flags;
+  a.first = 0;
+  a.count = -1;
+  a.n_adjust = 0;
   const bool timed = c->time_kernels && c->pev_used < qmc_ctx::NEV;
   if (timed) CK(cudaEventRecord(c->pev0[c->pev_used], c->stream));
-  CK(launch_propagate_v2(c->ksel, c->cfg, c->stream, c->plan, c->dmc, a, c->e_old));
+  CK(launch_propagate_v2(c->ksel, c->cfg, c->cfg.grid, c->stream, c->plan, c->dmc, a, c->e_old));
   if (timed) CK(cudaEventRecord(c->pev1[c->pev_used++], c->stream));
+  c->launches += 1;
+  if (c->nranks > 1 && c->dmc.branching_on && c->pops_pending)
+    { /* one step late, like dmcDriver::isend (dmcDriver.cpp:112,150-157): while the move kernel runs, the host reads the
+         populations the previous step's all-reduce delivered and posts the transfers on the communication stream */
+      if (c->ar_pending) CK(cudaEventSynchronize(c->ev_ar));
+      c->pops_pending = false;
+      if (++c->mig_phase % c->mig_every == 0)
+        {
+          std::vector<int> src, amt;
+          int n_send = 0, n_recv = 0;
+          plan_migration(c, src, amt, n_send, n_recv);
+          if (n_send > 0 || n_recv > 0)
+            {
+              const size_t dofs = c->plan.dofs, wsz = 2 * dofs + 2;
+              CK(launch_pack_tail(c->comm_stream, a.in, c->parent, c->ctl, (int)dofs, n_send, c->slab_send));
+              NK(g_nccl.GroupStart());
+              size_t off = 0;
+              for (int r = 0; r < c->nranks; ++r)
+                if (amt[r] > 0 && src[r] == c->rank)
+                  {
+                    NK(g_nccl.Send(c->slab_send + off, (size_t)amt[r] * wsz, NCCL_FLOAT64, r, c->comm, c->comm_stream));
+                    off += (size_t)amt[r] * wsz;
+                  }
+              if (n_recv > 0) NK(g_nccl.Recv(c->slab_recv, (size_t)n_recv * wsz, NCCL_FLOAT64, src[c->rank], c->comm, c->comm_stream));
+              NK(g_nccl.GroupEnd());
+              CK(launch_unpack_append(c->comm_stream, a.in, c->parent, c->ctl, (int)dofs, n_recv, c->slab_recv));
+              CK(cudaEventRecord(c->ev_mig, c->comm_stream));
+              CK(cudaStreamWaitEvent(c->stream, c->ev_mig, 0));
+              if (n_recv > 0)
+                { /* late arrivals are advanced within the same step (ptools.cpp:379-394, dmcDriver.cpp:133-136) */
+                  StepArgs t = a;
+                  t.first = -1;
+                  t.count = n_recv;
+                  const int g = std::max(1, std::min(c->cfg.grid, (n_recv + c->cfg.groups_per_cta - 1) / c->cfg.groups_per_cta));
+                  CK(launch_propagate_v2(c->ksel, c->cfg, g, c->stream, c->plan, c->dmc, t, c->e_old));
+                  c->launches += 1;
+                }
+              a.n_adjust = n_recv - n_send;
+              c->launches += (n_send > 0) + (n_recv > 0);
+              c->mig_events += 1;
+              c->mig_out += n_send;
+              c->mig_in += n_recv;
+            }
+        }
+    }
   if (c->ar_pending) CK(cudaStreamWaitEvent(c->stream, c->ev_ar, 0));        /* scan needs E_T of the previous population */
-  CK(launch_scan_v2(c->stream, c->dmc, a, c->e_old, c->n_partials, c->nranks > 1));
-  c->launches += 2;
+  CK(launch_scan_v2(c->stream, c->dmc, a, c->e_old, c->nranks > 1));
+  c->launches += 1;
   c->cur ^= 1;
   if (c->nranks > 1)
     {
       CK(cudaEventRecord(c->ev_scan, c->stream));
       CK(cudaStreamWaitEvent(c->comm_stream, c->ev_scan, 0));
-      NK(g_nccl.AllReduce(c->ctl->lsum, c->ctl->gsum, 2 + MAX_RANKS, NCCL_FLOAT64, NCCL_SUM, c->comm, c->comm_stream));
+      NK(g_nccl.AllReduce(c->ctl->lsum, c->ctl->gsum, NSUM, NCCL_FLOAT64, NCCL_SUM, c->comm, c->comm_stream));
+      CK(cudaMemcpyAsync(c->h_sums, c->ctl->gsum, sizeof(double) * NSUM, cudaMemcpyDeviceToHost, c->comm_stream));
       CK(cudaEventRecord(c->ev_ar, c->comm_stream));
       c->ar_pending = true;
+      c->pops_pending = true;
     }
   if (accumulate && c->has_hist)
     {
@@ -1006,14 +1101,24 @@ int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, co
       cudaEventCreate(&c->pev1[i]);
     }
   if (const char *pv = getenv("QMC4_PIPELINE"))
-    if (atoi(pv) == 2)
-      {
-        c->pipeline = 2;
-        if ((e = configure_kernels_v2(c->max_smem)) != cudaSuccess) return bail(std::string("kernel image (v2): ") + cudaGetErrorString(e));
-        if ((e = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
-        cudaEventCreateWithFlags(&c->ev_scan, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&c->ev_ar, cudaEventDisableTiming);
-      }
+    if (atoi(pv) == 1) c->pipeline = 1;
+  if ((e = configure_kernels_v2(c->max_smem)) != cudaSuccess) return bail(std::string("kernel image (v2): ") + cudaGetErrorString(e));
+  {
+    /* the communication stream outranks the compute stream: the 144-byte all-reduce of step k is enqueued before the
+       estimator / move kernels that follow the scan, and its CTA is placed first */
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    cudaEventCreateWithFlags(&c->ev_scan, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_ar, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_mig, cudaEventDisableTiming);
+    if ((e = cudaHostAlloc((void **)&c->h_sums, sizeof(double) * NSUM, cudaHostAllocDefault)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    memset(c->h_sums, 0, sizeof(double) * NSUM);
+  }
+  if (const char *v = getenv("QMC4_MIGRATE_EVERY"))
+    c->mig_every = std::max(1, atoi(v));
+  if (const char *v = getenv("QMC4_MIGRATE_BAND"))
+    c->mig_band = std::max(0.0, atof(v));
   if ((e = cudaMalloc(&c->ctl, sizeof(Ctl))) != cudaSuccess) return bail(cudaGetErrorString(e));
   cudaMemset(c->ctl, 0, sizeof(Ctl));
   memset(&c->dmc, 0, sizeof c->dmc);
@@ -1034,8 +1139,12 @@ void qmc_destroy(qmc_ctx *c)
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->e_old);
+  cudaFree(c->flags);
+  cudaFree(c->d_checksum);
+  if (c->h_sums) cudaFreeHost(c->h_sums);
   if (c->ev_scan) cudaEventDestroy(c->ev_scan);
   if (c->ev_ar) cudaEventDestroy(c->ev_ar);
+  if (c->ev_mig) cudaEventDestroy(c->ev_mig);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   for (int b = 0; b < 2; ++b)
     {
@@ -1227,7 +1336,7 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
 {
   if (!c) return 1;
   if (c->planned) return fail(c, "qmc_set_dmc called twice");
-  if (c->genealogy() || c->force_energy) c->pipeline = 1;
+  if (c->genealogy() || c->force_energy) c->pipeline = 1;      /* records / forceEnergy ride on the fused pipeline */
   if (c->force_energy && branching_on)
     /* main.cpp attaches the forceEnergy estimator to vmcDriver (:318-335) and to dmcDriver only for svmc (:395-408) */
     return fail(c, "forceEnergy is measured by the methods without branching (vmc, svmc), as in the reference");
@@ -1274,11 +1383,18 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
   if (c->nranks > 1)
     { /* migration slabs sized once for a quarter of the capacity: no cudaMalloc/cudaFree (device-wide
          synchronisation) between the ranks' NCCL calls of qmc_rebalance in the common case */
-      c->slab_bytes = (size_t)(capacity / 4 + 1) * (2 * dofs + 2) * 8;
+      c->slab_walkers = (int)(capacity / 4 + 1);
+      c->slab_bytes = (size_t)c->slab_walkers * (2 * dofs + 2) * 8;
       CK(cudaMalloc(&c->slab_send, c->slab_bytes));
       CK(cudaMalloc(&c->slab_recv, c->slab_bytes));
     }
-  if (c->pipeline == 2) CK(cudaMalloc(&c->e_old, capacity * 8));
+  if (c->pipeline == 2)
+    {
+      CK(cudaMalloc(&c->e_old, capacity * 8));
+      CK(cudaMalloc(&c->flags, capacity * 4));
+      CK(cudaMemset(c->flags, 0, capacity * 4));
+    }
+  CK(cudaMalloc(&c->d_checksum, 8));
   c->cfg.grid = grid_for(c, capacity);
   c->n_partials = c->cfg.grid * c->cfg.groups_per_cta;
   CK(cudaMalloc(&c->partials, (size_t)c->n_partials * 2 * 8));
@@ -1513,6 +1629,16 @@ int qmc_upload_walkers(qmc_ctx *c, const double *R, int64_t nW)
   Ctl h;
   CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (c->nranks > 1)
+    { /* the migration planner of the first step reads these populations; every rank must own the same number of slots
+         (the plan is clamped to the receivers' free slots and to the slab size, identically on every rank) */
+      memcpy(c->h_sums, h.gsum, sizeof(double) * NSUM);
+      c->pops_pending = true;
+      c->ar_pending = false;
+      for (int r = 1; r < c->nranks; ++r)      /* free slots + population = capacity of rank r */
+        if (h.gsum[2 + MAX_RANKS + r] + h.gsum[2 + r] != h.gsum[2 + MAX_RANKS] + h.gsum[2])
+          return fail(c, "every rank must be given the same capacity (qmc_set_dmc)");
+    }
   if (h.invalid_init) return fail(c, "Inalid initial configurations.");   /* dmcDriver.cpp:166-170 (sic) */
   return 0;
 }
@@ -1640,13 +1766,14 @@ int qmc_block_results(qmc_ctx *c, qmc_block_result *out)
   Ctl h;
   CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  double v[4] = {h.blk_esum, h.blk_ecount, h.blk_moves, h.blk_acc};
+  /* the overflow flag travels with the sums: every rank sees it, so the host driver's error is collective too */
+  double v[5] = {h.blk_esum, h.blk_ecount, h.blk_moves, h.blk_acc, (double)(h.overflow != 0)};
   if (c->nranks > 1)
     {
       if (ensure_scratch(c, 64, 0)) return 1;
-      CK(cudaMemcpyAsync(c->scr, v, 32, cudaMemcpyHostToDevice, c->stream));
-      NK(g_nccl.AllReduce(c->scr, c->scr, 4, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
-      CK(cudaMemcpyAsync(v, c->scr, 32, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(c->scr, v, 40, cudaMemcpyHostToDevice, c->stream));
+      NK(g_nccl.AllReduce(c->scr, c->scr, 5, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+      CK(cudaMemcpyAsync(v, c->scr, 40, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
     }
   out->energy_sum = v[0];
@@ -1662,7 +1789,7 @@ int qmc_block_results(qmc_ctx *c, qmc_block_result *out)
     out->energy_shift = D.branching_on ? e : 0.0;
   }
   out->steps_done = h.blk_steps;
-  out->overflow = h.overflow;
+  out->overflow = v[4] != 0.0;
   out->device_ms = c->device_ms;
   c->device_ms = 0;
   CK(cudaMemsetAsync(&c->ctl->blk_esum, 0, 5 * 8, c->stream));
@@ -1944,6 +2071,15 @@ int migrate_records(qmc_ctx *c, const std::vector<int> &src, const std::vector<i
 }
 } // namespace
 
+int qmc_set_migration(qmc_ctx *c, int every, double band)
+{
+  if (!c) return 1;
+  if (every < 1 || !(band >= 0.0)) return fail(c, "qmc_set_migration: every >= 1, band >= 0");
+  c->mig_every = every;
+  c->mig_band = band;
+  return 0;
+}
+
 int qmc_rebalance(qmc_ctx *c, int64_t *moved)
 {
   if (!c) return 1;
@@ -1952,38 +2088,58 @@ int qmc_rebalance(qmc_ctx *c, int64_t *moved)
   if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   if (c->nranks == 1) return 0;
   cudaSetDevice(c->device);
-  if (c->pipeline == 2 && sync_all(c)) return 1;
+  if (sync_all(c)) return 1;
   Ctl h;
   CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  // populations of every rank: the one-hot vector carried by the per-step all-reduce
-  std::vector<int> pops(c->nranks), src(c->nranks), amt(c->nranks);
-  for (int r = 0; r < c->nranks; ++r) pops[r] = (int)h.gsum[2 + r];
-  if (pops[c->rank] != h.n_cur) return fail(c, "population vector out of date");
-  qmc_plan_rebalance(pops.data(), c->nranks, src.data(), amt.data());
+  // Fresh populations of every rank, gathered here as the reference does inside isendReceive (ptools.cpp:244-268): the
+  // vector carried by the per-step all-reduce is stale after a previous rebalance.  Every rank also publishes its free
+  // slots, so that ALL ranks take the same decision (plan or refuse) before any Send/Recv is posted.
+  const int nr = c->nranks;
+  if (ensure_scratch(c, 0, (size_t)(nr + 1) * 4 * sizeof(int))) return 1;
+  int mine[4] = {h.n_cur, h.n_prev, (int)c->cap, 0};
+  std::vector<int> all((size_t)nr * 4);
+  CK(cudaMemcpyAsync(c->scr_i + (size_t)nr * 4, mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+  NK(g_nccl.AllGather(c->scr_i + (size_t)nr * 4, c->scr_i, 4, NCCL_INT32, c->comm, c->stream));
+  CK(cudaMemcpyAsync(all.data(), c->scr_i, all.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  std::vector<int> pops(nr), src(nr), amt(nr);
+  for (int r = 0; r < nr; ++r) pops[r] = all[4 * r];
+  qmc_plan_rebalance(pops.data(), nr, src.data(), amt.data());
+  for (int r = 0; r < nr; ++r)      /* identical on every rank: nobody enters the exchange if one receiver cannot take its share */
+    if (amt[r] > 0 && all[4 * r + 1] + amt[r] > all[4 * r + 2])
+      return fail(c, "rebalance: capacity exceeded on rank " + std::to_string(r) + " (" + std::to_string(all[4 * r + 1]) + " slots in use + " +
+                         std::to_string(amt[r]) + " arriving > capacity " + std::to_string(all[4 * r + 2]) + ")");
   const size_t dofs = c->plan.dofs, wsz = 2 * dofs + 2;
   int n_send = 0;
-  for (int r = 0; r < c->nranks; ++r)
+  for (int r = 0; r < nr; ++r)
     if (amt[r] > 0 && src[r] == c->rank) n_send += amt[r];
   const int n_recv = amt[c->rank];
+  // from here on a local failure would leave the peers blocked in the exchange: abort the communicator so they error out
+  auto fatal = [&](const std::string &m) {
+    if (c->comm) g_nccl.CommAbort(c->comm);
+    c->comm = nullptr;
+    return fail(c, m + " (communicator aborted)");
+  };
   const size_t need = (size_t)std::max(n_send, n_recv) * wsz * 8;
   if (need > c->slab_bytes)
     {
       cudaFree(c->slab_send);
       cudaFree(c->slab_recv);
       c->slab_send = c->slab_recv = nullptr;
-      CK(cudaMalloc(&c->slab_send, need));
-      CK(cudaMalloc(&c->slab_recv, need));
+      c->slab_bytes = 0;
+      if (cudaMalloc(&c->slab_send, need) != cudaSuccess || cudaMalloc(&c->slab_recv, need) != cudaSuccess)
+        return fatal("rebalance: cannot allocate " + std::to_string(need >> 20) + " MiB of migration slabs");
       c->slab_bytes = need;
     }
   int n_cur = h.n_cur;
-  if (n_recv > 0 && h.n_prev + n_recv > c->cap) return fail(c, "rebalance: capacity exceeded");
-  // senders ship their TAIL walkers (ptools.cpp:297-303)
-  if (n_send > 0) CK(launch_pack(c->stream, c->buf[c->cur], c->parent, (int)dofs, n_cur - n_send, n_send, c->slab_send));
+  // senders ship their TAIL walkers (ptools.cpp:297-303); same kernels as the in-step migration of qmc_step
+  if (n_send > 0 && launch_pack_tail(c->stream, c->buf[c->cur], c->parent, c->ctl, (int)dofs, n_send, c->slab_send) != cudaSuccess)
+    return fatal("rebalance: pack kernel launch failed");
   NK(g_nccl.GroupStart());
   {
     size_t off = 0;
-    for (int r = 0; r < c->nranks; ++r)
+    for (int r = 0; r < nr; ++r)
       if (amt[r] > 0 && src[r] == c->rank)
         {
           NK(g_nccl.Send(c->slab_send + off, (size_t)amt[r] * wsz, NCCL_FLOAT64, r, c->comm, c->stream));
@@ -1992,14 +2148,12 @@ int qmc_rebalance(qmc_ctx *c, int64_t *moved)
     if (n_recv > 0) NK(g_nccl.Recv(c->slab_recv, (size_t)n_recv * wsz, NCCL_FLOAT64, src[c->rank], c->comm, c->stream));
   }
   NK(g_nccl.GroupEnd());
-  if (c->genealogy() && c->fw_event > 0 && migrate_records(c, src, amt, n_send, n_recv, n_cur)) return 1;
+  if (c->genealogy() && c->fw_event > 0 && migrate_records(c, src, amt, n_send, n_recv, n_cur)) return fatal("rebalance: " + c->err);
   n_cur -= n_send;
   if (n_recv > 0)
     { // received walkers land in free physical slots [n_prev, n_prev+n_recv) and are appended to the population
-      CK(launch_unpack(c->stream, c->buf[c->cur], (int)dofs, h.n_prev, n_recv, c->slab_recv));
-      std::vector<int> par(n_recv);
-      for (int i = 0; i < n_recv; ++i) par[i] = h.n_prev + i;
-      CK(cudaMemcpyAsync(c->parent + n_cur, par.data(), (size_t)n_recv * 4, cudaMemcpyHostToDevice, c->stream));
+      if (launch_unpack_append(c->stream, c->buf[c->cur], c->parent, c->ctl, (int)dofs, n_recv, c->slab_recv) != cudaSuccess)
+        return fatal("rebalance: unpack kernel launch failed");
       CK(cudaStreamSynchronize(c->stream));
       n_cur += n_recv;
     }
@@ -2007,9 +2161,20 @@ int qmc_rebalance(qmc_ctx *c, int64_t *moved)
   CK(cudaMemcpyAsync(&c->ctl->n_cur, &n_cur, 4, cudaMemcpyHostToDevice, c->stream));
   c->n_host = n_cur;
   CK(cudaMemcpyAsync(&c->ctl->n_prev, &np, 4, cudaMemcpyHostToDevice, c->stream));
-  double newpop = n_cur;
-  CK(cudaMemcpyAsync(&c->ctl->gsum[2 + c->rank], &newpop, 8, cudaMemcpyHostToDevice, c->stream));
+  // the whole population vector is refreshed (every rank knows the plan), not only this rank's entry
+  std::vector<double> newpops(nr);
+  for (int r = 0; r < nr; ++r) newpops[r] = (double)pops[r] + amt[r];
+  for (int r = 0; r < nr; ++r)
+    if (amt[r] > 0) newpops[src[r]] -= amt[r];
+  CK(cudaMemcpyAsync(&c->ctl->gsum[2], newpops.data(), (size_t)nr * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  c->pops_pending = false;           /* balanced now: the in-step planner waits for the next all-reduce */
+  if (n_send > 0 || n_recv > 0)
+    {
+      c->mig_events += 1;
+      c->mig_out += n_send;
+      c->mig_in += n_recv;
+    }
   c->launches += 2;
   if (moved) *moved = (int64_t)n_send - n_recv;
   return 0;
@@ -2116,6 +2281,23 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "warps_per_walker") *value = c->cfg.nwarps_per_group;
   else if (k == "kernel_variant") *value = c->ksel;
   else if (k == "pipeline") *value = c->pipeline;
+  else if (k == "migration_events") *value = (double)c->mig_events;
+  else if (k == "migrated_out") *value = (double)c->mig_out;
+  else if (k == "migrated_in") *value = (double)c->mig_in;
+  else if (k == "migrate_every") *value = c->mig_every;
+  else if (k == "migrate_band") *value = c->mig_band;
+  else if (k == "population_checksum")
+    { /* order-independent fingerprint of this rank's population, low 52 bits (exact in a double; additive over ranks mod 2^52) */
+      if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
+      cudaSetDevice(c->device);
+      if (sync_all(c)) return 1;
+      unsigned long long hsum = 0;
+      CK(cudaMemsetAsync(c->d_checksum, 0, 8, c->stream));
+      CK(launch_population_checksum(c->stream, c->buf[c->cur], c->parent, c->ctl, c->d_checksum));
+      CK(cudaMemcpyAsync(&hsum, c->d_checksum, 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      *value = (double)(hsum & ((1ull << 52) - 1));
+    }
   else if (k == "ctas_per_sm") *value = propagate_occupancy(c->ksel, c->has_hist, c->cfg.smem);
   else if (k == "launches") *value = (double)c->launches;
   else if (k == "sms") *value = c->sms;

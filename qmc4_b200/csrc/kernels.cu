@@ -375,7 +375,11 @@ scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent
         }
       ctl->lsum[0] = s_e[0];
       ctl->lsum[1] = (double)newW;
-      for (int r = 0; r < MAX_RANKS; ++r) ctl->lsum[2 + r] = (r == dmc.rank) ? (double)newW : 0.0;
+      for (int r = 0; r < MAX_RANKS; ++r)
+        {
+          ctl->lsum[2 + r] = (r == dmc.rank) ? (double)newW : 0.0;
+          ctl->lsum[2 + MAX_RANKS + r] = (r == dmc.rank) ? (double)(a.cap - max(W, newW)) : 0.0;
+        }
       if (a.accumulate)
         {
           ctl->blk_esum += s_e[0];
@@ -384,7 +388,7 @@ scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent
         }
       if (!multi_rank)
         {
-          for (int r = 0; r < 2 + MAX_RANKS; ++r) ctl->gsum[r] = ctl->lsum[r];
+          for (int r = 0; r < NSUM; ++r) ctl->gsum[r] = ctl->lsum[r];
           if (dmc.branching_on) ctl->eshift = branch_shift(dmc, s_e[0], (double)newW);
         }
     }

@@ -26,6 +26,10 @@ struct WalkerBuf {
 };
 
 constexpr int MAX_RANKS = 8;
+// per-step reduction vector: {sum E, population, one-hot populations[MAX_RANKS], one-hot free walker slots[MAX_RANKS]}.
+// One all-reduce (sum) of it gives every rank the E_T inputs (branching.cpp:75-76) and what the migration planner needs
+// (ptools.cpp:244-268 allgathers the populations): 144 bytes.
+constexpr int NSUM = 2 + 2 * MAX_RANKS;
 
 // Device-resident control block: everything the step sequence needs lives here so that
 // qmc_step() enqueues kernels without ever reading back (population, E_T, counters).
@@ -36,8 +40,8 @@ struct Ctl {
   int n_prev;                  // physical slots [0,n_prev) of the current buffer are referenced by the parent map
   unsigned long long step;     // global step counter (Philox counter word)
   double eshift;               // E_T in use  (branching.cpp:65-97)
-  double lsum[2 + MAX_RANKS];  // local  {sum E, population, one-hot population vector}
-  double gsum[2 + MAX_RANKS];  // global {sum E, population, populations per rank} (after all-reduce)
+  double lsum[NSUM];           // local  {sum E, population, one-hot population vector, one-hot free slots}
+  double gsum[NSUM];           // global {sum E, population, populations per rank, free slots per rank} (after all-reduce)
   double blk_esum, blk_ecount; // energy estimator (scalarAccumulator, accumulators.h:21-47)
   double blk_moves, blk_acc;   // metropolis counters (metropolis.cpp:24-26)
   double blk_steps;
@@ -60,6 +64,10 @@ struct StepArgs {
   int accumulate;              // sampling step: estimators on
   int cap;
   TraceDev trace;
+  // pipeline 2 (kernels_v2.cu)
+  int *flags;                  // [cap] bit 0: move accepted (the scan counts the Metropolis statistics from these)
+  int first, count;            // move kernel: walkers [first, first+count); count < 0: [0, ctl->n_cur).  first < 0: first = ctl->n_cur
+  int n_adjust;                // scan: population moved this step = ctl->n_cur + n_adjust (arrivals - departures of the migration)
 };
 
 struct EvalArgs {
@@ -97,12 +105,15 @@ int eval_regs(int ksel, bool hist);
 int propagate_occupancy(int ksel, bool hist, size_t smem);
 double measure_fp64_peak_tflops(cudaStream_t st, float *ms_out);
 
-// experimental pipeline 2 (kernels_v2.cu, QMC4_PIPELINE=2)
+// pipeline 2 (kernels_v2.cu): the production step sequence
 cudaError_t configure_kernels_v2(int max_smem_optin);
 int propagate_v2_occupancy(int ksel, size_t smem);
-cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const DmcParams &dmc,
+cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, int grid, cudaStream_t st, const Plan &plan, const DmcParams &dmc,
                                 const StepArgs &a, double *e_old);
-cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int n_partials, int multi_rank);
+cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int multi_rank);
+cudaError_t launch_pack_tail(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, int dofs, int n_send, double *slab);
+cudaError_t launch_unpack_append(cudaStream_t st, const WalkerBuf &buf, int *parent, const Ctl *ctl, int dofs, int n_recv, const double *slab);
+cudaError_t launch_population_checksum(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, unsigned long long *out);
 cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const WalkerBuf &buf, const int *parent,
                               const Ctl *ctl, double *hist, int occ, int grid);
 int estimator_occupancy(int occ, size_t smem);

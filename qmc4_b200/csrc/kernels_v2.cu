@@ -1,18 +1,17 @@
-// kernels_v2.cu — EXPERIMENTAL step pipeline ("pipeline 2"), selected with QMC4_PIPELINE=2.
-// NOT the default and NOT yet validated on hardware (written after the round-1 GPU budget was
-// spent): the default pipeline of kernels.cu is untouched by this file.
+// kernels_v2.cu — the production step pipeline ("pipeline 2"; pipeline 1 of kernels.cu is kept for the traced step and
+// for runs that carry genealogical records).  Bitwise identical trajectories to pipeline 1 (tests/test_pipeline2.py).
 //
-// Why: in pipeline 1 `propagate_kernel` needs E_T (for nDescendants) and therefore the per-step
-// all-reduce sits on the critical path (35-60 us of a 0.34 ms step at 8 GPUs), and the g(r) pass runs
-// inside the register-heavy propagate kernel.  Pipeline 2 reorders the step:
-//     propagate_v2 (no E_T, no estimators; writes E_old per walker)
-//  -> scan_v2      (computes nDescendants = int(exp(-tau(E'+E)/2 - E_T)) + u) with the SAME Philox
-//                   draw pipeline 1 uses, so trajectories are bitwise identical; prefix sum,
-//                   parent map, sums)                                  [waits for all-reduce k-1]
-//  -> all-reduce k on a second stream, overlapped with
-//  -> estimator_kernel (post-branching population, unit weight: dmcDriver::accumulate,
-//                   dmcDriver.cpp:257-264, exactly as the reference iterates it) and with
-//     propagate_v2 of step k+1.
+//     move_kernel      one DMC move per walker, needs neither E_T nor the estimators: gather the parent (branching copy/kill
+//                      fused into the load) -> drift + diffusion (dmcMoves.cpp:12-30) -> evaluation -> Green ratio
+//                      (dmcMoves.cpp:32-57) -> Metropolis (metropolis.cpp:5-29) -> commit or carry the parent through
+//                      (dmcDriver.cpp:56-84); writes E' , E and the accepted flag per walker
+//  -> scan_v2_kernel   nDescendants = int(exp(-tau((E'+E)/2 - E_T)) + u) (branching.cpp:11-14) with the Philox draw of the
+//                      walker, prefix sum -> parent map, sums, E_T inputs                 [waits for all-reduce k-1]
+//  -> all-reduce k     of {sum E, W, populations, free slots} on the communication stream, overlapped with
+//  -> estimator_kernel (post-branching population with unit weight, exactly what dmcDriver::accumulate iterates,
+//                      dmcDriver.cpp:257-264) and with move_kernel of step k+1;
+//  migration (ptools.cpp:271-401, one step late like dmcDriver.cpp:112,150-157): pack_tail_kernel -> ncclSend/Recv ->
+//  unpack_append_kernel on the communication stream while move_kernel(k+1) runs, then move_kernel on the arrivals only.
 #include "kernels.cuh"
 #include "evaluate.cuh"
 #include "kernel_common.cuh"
@@ -23,8 +22,8 @@ namespace {
 
 template <int JK, int VK>
 __global__ void __launch_bounds__(CTA_THREADS, QMC_MIN_BLOCKS)
-propagate_v2_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams dmc, const StepArgs a, double *e_old,
-                    int nwarps_per_group, size_t group_bytes)
+move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams dmc, const StepArgs a, double *e_old,
+            int nwarps_per_group, size_t group_bytes)
 {
   QMC_DYNAMIC_SMEM(smem);
   const Group G = make_group(nwarps_per_group);
@@ -33,12 +32,13 @@ propagate_v2_kernel(const __grid_constant__ Plan plan, const __grid_constant__ D
   const Scratch S = make_scratch(plan, smem, g, nwarps_per_group, group_bytes);
   const int dofs = plan.dofs;
   const Ctl *ctl = a.ctl;
-  const int nW = ctl->n_cur;
+  /* walkers [j0, j1): the whole population, or the walkers that arrived by migration during this step */
+  const int j0 = a.count < 0 ? 0 : (a.first < 0 ? ctl->n_cur : a.first);
+  const int j1 = a.count < 0 ? ctl->n_cur : j0 + a.count;
   const unsigned long long step = ctl->step;
   const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
-  double n_moves = 0, n_acc = 0;
 
-  for (int j = blockIdx.x * groups + g; j < nW; j += gridDim.x * groups)
+  for (int j = j0 + blockIdx.x * groups + g; j < j1; j += gridDim.x * groups)
     {
       const int src = a.parent[j];
       const double *Rold = a.in.R + (size_t)src * dofs;
@@ -86,7 +86,7 @@ propagate_v2_kernel(const __grid_constant__ Plan plan, const __grid_constant__ D
       const double Eold = a.in.E[src];
       const u32x4 rd = philox4x32_10({(uint32_t)j, 0xffffffffu, step_lo, step_hi}, dmc.seed_lo, dmc.seed_hi);
       const double u_m = u01_53(rd.x, rd.y);
-      const double A = 2.0 * (r.logpsi - lp_old) + qs;
+      const double A = 2.0 * (r.logpsi - lp_old) + (dmc.vmc ? 0.0 : qs);     /* vmc: vmcDriver.cpp:68 */
       const bool accepted = r.valid && (A > 0.0 || A > log(u_m));
       const double Efin = accepted ? Enew : Eold;
       double *Rout = a.out.R + (size_t)j * dofs;
@@ -108,16 +108,9 @@ propagate_v2_kernel(const __grid_constant__ Plan plan, const __grid_constant__ D
           a.out.logpsi[j] = accepted ? r.logpsi : lp_old;
           a.out.E[j] = Efin;
           e_old[j] = Eold;            /* branching needs (E' + E)/2 (branching.cpp:13); decided in scan_v2 */
-          n_moves += 1;
-          n_acc += accepted ? 1 : 0;
+          a.flags[j] = accepted ? 1 : 0;
         }
       G.sync();
-    }
-  if (G.gtid == 0)
-    {
-      double *p = a.partials + ((size_t)blockIdx.x * groups + g) * 2;
-      p[0] = n_moves;
-      p[1] = n_acc;
     }
 }
 
@@ -125,13 +118,13 @@ constexpr int SCAN2_THREADS = 1024;
 
 // scan_kernel of pipeline 1 + the branching decision (nDescendants) it used to receive from propagate.
 __global__ void __launch_bounds__(SCAN2_THREADS)
-scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const double *e_old, int *parent_next, int n_partials, int multi_rank)
+scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const double *e_old, int *parent_next, int multi_rank)
 {
   __shared__ int s_warp[32];
   __shared__ double s_e[SCAN2_THREADS], s_mv[SCAN2_THREADS], s_ac[SCAN2_THREADS];
   __shared__ int s_carry, s_tile;
   Ctl *ctl = a.ctl;
-  const int W = ctl->n_cur;
+  const int W = ctl->n_cur + a.n_adjust;     /* walkers moved this step: migration removed the tail / appended the arrivals */
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const unsigned long long step = ctl->step;
   const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
@@ -139,7 +132,7 @@ scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const do
   if (t == 0) s_carry = 0;
   __syncthreads();
   double esum = 0;
-  int dropped = 0;
+  int dropped = 0, nacc = 0;
   for (int base = 0; base < W; base += 4 * SCAN2_THREADS)
     {
       const int j0 = base + 4 * t;
@@ -154,6 +147,7 @@ scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const do
           if (j < W)
             {
               e[u] = a.out.E[j];
+              nacc += a.flags[j] & 1;
               int nn = 1;
               if (dmc.branching_on)
                 {
@@ -221,17 +215,9 @@ scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const do
       total = 1;
     }
   if (dropped) ctl->overflow = 1;
-  {
-    double mv = 0, ac = 0;
-    for (int i = t; i < n_partials; i += SCAN2_THREADS)
-      {
-        mv += a.partials[2 * i];
-        ac += a.partials[2 * i + 1];
-      }
-    s_e[t] = esum;
-    s_mv[t] = mv;
-    s_ac[t] = ac;
-  }
+  s_e[t] = esum;
+  s_mv[t] = 0;
+  s_ac[t] = (double)nacc;      /* small integers: exact in any order */
   __syncthreads();
   for (int d = SCAN2_THREADS / 2; d >= 1; d >>= 1)
     {
@@ -249,12 +235,16 @@ scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const do
       ctl->n_prev = W;
       ctl->n_cur = newW;
       ctl->step += 1;
-      ctl->blk_moves += s_mv[0];
+      ctl->blk_moves += (double)W;
       ctl->blk_acc += s_ac[0];
       ctl->blk_steps += 1;
       ctl->lsum[0] = s_e[0];
       ctl->lsum[1] = (double)newW;
-      for (int r = 0; r < MAX_RANKS; ++r) ctl->lsum[2 + r] = (r == dmc.rank) ? (double)newW : 0.0;
+      for (int r = 0; r < MAX_RANKS; ++r)
+        {
+          ctl->lsum[2 + r] = (r == dmc.rank) ? (double)newW : 0.0;
+          ctl->lsum[2 + MAX_RANKS + r] = (r == dmc.rank) ? (double)(a.cap - max(W, newW)) : 0.0;
+        }
       if (a.accumulate)
         {
           ctl->blk_esum += s_e[0];
@@ -263,7 +253,7 @@ scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const do
         }
       if (!multi_rank)
         {
-          for (int r = 0; r < 2 + MAX_RANKS; ++r) ctl->gsum[r] = ctl->lsum[r];
+          for (int r = 0; r < NSUM; ++r) ctl->gsum[r] = ctl->lsum[r];
           if (dmc.branching_on) ctl->eshift = branch_shift(dmc, s_e[0], (double)newW);
         }
     }
@@ -304,14 +294,75 @@ estimator_kernel(const __grid_constant__ Plan plan, const WalkerBuf buf, const i
   hist_fx_flush(plan, H.fx, H.base);
 }
 
+
+// Migration (walkerDistribution, ptools.cpp:271-401): senders ship their TAIL walkers (:297-303), receivers append (:307-324).
+// The kernels index through the control block, so the host only needs the plan (who sends how many to whom), which it derives
+// from the all-reduced population vector.  Slab record = {R[dofs], F[dofs], log psi, E}.
+__global__ void pack_tail_kernel(WalkerBuf buf, const int *parent, const Ctl *ctl, int dofs, int n_send, double *slab)
+{
+  const int first = ctl->n_cur - n_send;
+  for (int w = blockIdx.x; w < n_send; w += gridDim.x)
+    {
+      double *dst = slab + (size_t)w * (2 * dofs + 2);
+      const int p = parent[first + w];
+      const size_t s = (size_t)p * dofs;
+      for (int k = threadIdx.x; k < dofs; k += blockDim.x)
+        {
+          dst[k] = buf.R[s + k];
+          dst[dofs + k] = buf.F[s + k];
+        }
+      if (threadIdx.x == 0)
+        {
+          dst[2 * dofs] = buf.logpsi[p];
+          dst[2 * dofs + 1] = buf.E[p];
+        }
+    }
+}
+// arrivals land in the free physical slots [n_prev, n_prev + n_recv) and are appended to the population at [n_cur, n_cur + n_recv)
+__global__ void unpack_append_kernel(WalkerBuf buf, int *parent, const Ctl *ctl, int dofs, int n_recv, const double *slab)
+{
+  const int slot0 = ctl->n_prev, idx0 = ctl->n_cur;
+  for (int w = blockIdx.x; w < n_recv; w += gridDim.x)
+    {
+      const double *src = slab + (size_t)w * (2 * dofs + 2);
+      const size_t s = (size_t)(slot0 + w) * dofs;
+      for (int k = threadIdx.x; k < dofs; k += blockDim.x)
+        {
+          buf.R[s + k] = src[k];
+          buf.F[s + k] = src[dofs + k];
+        }
+      if (threadIdx.x == 0)
+        {
+          buf.logpsi[slot0 + w] = src[2 * dofs];
+          buf.E[slot0 + w] = src[2 * dofs + 1];
+          parent[idx0 + w] = slot0 + w;
+        }
+    }
+}
+// order-independent fingerprint of the current population (conservation checks of the migration): sum over the walkers of the
+// 64-bit patterns of (log psi, E) mixed by an odd multiplier, wrapping arithmetic
+__global__ void population_checksum_kernel(WalkerBuf buf, const int *parent, const Ctl *ctl, unsigned long long *out)
+{
+  unsigned long long s = 0;
+  const int n = ctl->n_cur;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    {
+      const int p = parent[j];
+      const unsigned long long a = (unsigned long long)__double_as_longlong(buf.logpsi[p]);
+      const unsigned long long b = (unsigned long long)__double_as_longlong(buf.E[p]);
+      s += (a * 0x9E3779B97F4A7C15ull) ^ (b + 0xD1B54A32D192ED03ull);
+    }
+  if (s) atomicAdd(out, s);
+}
+
 #ifdef QMC_EMULATE   /* tests/emu: cudaLaunchKernel gets a trampoline that unpacks the argument array */
 template <int JK, int VK> void prop2_tramp(void **p)
 {
-  propagate_v2_kernel<JK, VK>(*(Plan *)p[0], *(DmcParams *)p[1], *(StepArgs *)p[2], *(double **)p[3], *(int *)p[4], *(size_t *)p[5]);
+  move_kernel<JK, VK>(*(Plan *)p[0], *(DmcParams *)p[1], *(StepArgs *)p[2], *(double **)p[3], *(int *)p[4], *(size_t *)p[5]);
 }
 template <int JK, int VK> const void *prop2() { return (const void *)&prop2_tramp<JK, VK>; }
 #else
-template <int JK, int VK> const void *prop2() { return (const void *)propagate_v2_kernel<JK, VK>; }
+template <int JK, int VK> const void *prop2() { return (const void *)move_kernel<JK, VK>; }
 #endif
 
 #ifdef QMC_EMULATE
@@ -368,18 +419,18 @@ int propagate_v2_occupancy(int ksel, size_t smem)
   return n < 1 ? 1 : n;
 }
 
-cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const DmcParams &dmc,
+cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, int grid, cudaStream_t st, const Plan &plan, const DmcParams &dmc,
                                 const StepArgs &a, double *e_old)
 {
   int nw = cfg.nwarps_per_group;
   size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
   void *args[] = {(void *)&plan, (void *)&dmc, (void *)&a, (void *)&e_old, (void *)&nw, (void *)&gb};
-  return cudaLaunchKernel(prop2_ptr(ksel), dim3(cfg.grid), dim3(cfg.block), args, cfg.smem, st);
+  return cudaLaunchKernel(prop2_ptr(ksel), dim3(grid), dim3(cfg.block), args, cfg.smem, st);
 }
 
-cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int n_partials, int multi_rank)
+cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int multi_rank)
 {
-  QMC_LAUNCH(scan_v2_kernel, 1, SCAN2_THREADS, 0, st, dmc, a, e_old, a.parent, n_partials, multi_rank);
+  QMC_LAUNCH(scan_v2_kernel, 1, SCAN2_THREADS, 0, st, dmc, a, e_old, a.parent, multi_rank);
   return cudaGetLastError();
 }
 
@@ -390,6 +441,24 @@ cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan 
   size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
   void *args[] = {(void *)&plan, (void *)&buf, (void *)&parent, (void *)&ctl, (void *)&hist, (void *)&nw, (void *)&gb};
   return cudaLaunchKernel(est_ptr(occ), dim3(grid), dim3(cfg.block), args, cfg.smem, st);
+}
+
+cudaError_t launch_pack_tail(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, int dofs, int n_send, double *slab)
+{
+  if (n_send <= 0) return cudaSuccess;
+  QMC_LAUNCH(pack_tail_kernel, n_send < 512 ? n_send : 512, 128, 0, st, buf, parent, ctl, dofs, n_send, slab);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack_append(cudaStream_t st, const WalkerBuf &buf, int *parent, const Ctl *ctl, int dofs, int n_recv, const double *slab)
+{
+  if (n_recv <= 0) return cudaSuccess;
+  QMC_LAUNCH(unpack_append_kernel, n_recv < 512 ? n_recv : 512, 128, 0, st, buf, parent, ctl, dofs, n_recv, slab);
+  return cudaGetLastError();
+}
+cudaError_t launch_population_checksum(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, unsigned long long *out)
+{
+  QMC_LAUNCH(population_checksum_kernel, 64, 256, 0, st, buf, parent, ctl, out);
+  return cudaGetLastError();
 }
 
 } // namespace qmc

@@ -90,6 +90,10 @@ static void runRank(const json_t &j, int rank, int nranks, const void *uid, int 
         { /* all walkers start from the same random configuration (main.cpp:380-388) */
           states_t states = generateRandomInitialConditions(Ns, lBoxInit, (unsigned long long)seed);
           for (size_t i = 0; i < nW / nranks; i++) dmcStates.push_back(states);
+          /* ... redrawn (same sequence on every rank) until the wavefunction's constraints are satisfied (main.cpp:253-266) */
+          dmcO.setInitialConditionGenerator([Ns, lBoxInit, seed](unsigned attempt) {
+            return generateRandomInitialConditions(Ns, lBoxInit, (unsigned long long)seed + 7919ull * attempt);
+          });
         }
       for (const auto &st : dmcStates)
         for (size_t s = 0; s < Ns.size(); ++s)

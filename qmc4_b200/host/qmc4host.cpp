@@ -420,13 +420,26 @@ void dmcDriver::run(const std::vector<states_t> &states, size_t nBlocks)
   speciesN = N;
   for (int n : N) dofs += 3 * n;
   std::vector<double> R(states.size() * (size_t)dofs);
-  for (size_t w = 0; w < states.size(); ++w)
-    {
-      size_t off = 0;
-      for (const auto &s : states[w])
+  auto flatten = [&](const states_t &st, size_t w) {
+    size_t off = 0;
+    for (const auto &s : st)
+      {
+        std::copy(s.begin(), s.end(), R.begin() + w * dofs + off);
+        off += s.size();
+      }
+  };
+  for (size_t w = 0; w < states.size(); ++w) flatten(states[w], w);
+  if (redraw)
+    { /* all walkers start from ONE random configuration (main.cpp:380-388), redrawn until psi.satisfyConstraints holds
+         (main.cpp:253-266); the constraint is evaluated by the device (qmc_eval's valid flag) */
+      for (unsigned attempt = 0;; ++attempt)
         {
-          std::copy(s.begin(), s.end(), R.begin() + w * dofs + off);
-          off += s.size();
+          int valid = 0;
+          check(qmc_eval(ctx, R.data(), 1, nullptr, nullptr, nullptr, nullptr, nullptr, &valid));
+          if (valid) break;
+          if (attempt >= 100000) throw invalidState("no random initial configuration satisfies the constraints of the wavefunction");
+          const states_t st = redraw(attempt + 1);
+          for (size_t w = 0; w < states.size(); ++w) flatten(st, w);
         }
     }
   if (master) writeWaveTables();

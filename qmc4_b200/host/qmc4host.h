@@ -605,6 +605,8 @@ class dmcDriver {
   void setDevice(int d) { device = d; }
   void setComm(const void *uniqueId, int rank_, int nranks_) { uid = uniqueId; rank = rank_; nranks = nranks_; }
   void setOutput(bool on) { master = on; }
+  /* random initial conditions are redrawn until the wavefunction's constraints hold (main.cpp:253-266): attempt k = 0, 1, ... */
+  void setInitialConditionGenerator(std::function<states_t(unsigned)> g) { redraw = std::move(g); }
   void run(const std::vector<states_t> &states, size_t nBlocks);
   double walkerMovesPerSecond() const { return moves / (deviceMs * 1e-3); }
 
@@ -624,6 +626,7 @@ class dmcDriver {
   bool performBranching = true, master = true, vmcMode = false;
   int device = 0, rank = 0, nranks = 1;
   const void *uid = nullptr;
+  std::function<states_t(unsigned)> redraw;
   qmc_ctx *ctx = nullptr;
   int dofs = 0;
   std::vector<int> speciesN;

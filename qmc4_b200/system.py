@@ -360,6 +360,10 @@ class System:
         self._ck(self.lib.qmc_rebalance(self.ctx, C.byref(m)))
         return m.value
 
+    def set_migration(self, every=1, band=0.005):
+        """in-step walker migration of qmc_step: plan every `every` steps, dead band `band` x mean population"""
+        self._ck(self.lib.qmc_set_migration(self.ctx, int(every), float(band)))
+
     def synchronize(self):
         self._ck(self.lib.qmc_synchronize(self.ctx))
 

@@ -148,6 +148,13 @@ def eval_cases():
     out["impurity"] = (impurity(), rng.uniform(-2.0, 2.0, size=(6, 36)))
     # dipolar_rep (jastrowDipolar.h: Bessel-K branch below matching_point, sin^alpha tail up to cut_off, flat beyond)
     out["jastrow_dipolar_rep"] = (pbc(18, 5.2, jastrow=DIPOLAR_REP), rng.uniform(-2.6, 2.6, size=(6, 54)))
+    # round 2 (appended last again): poschTellerPotential2b (potential.cpp:100-114) and the three-body terms at BASELINE
+    # config 4's size (N=32: one full 32-particle block)
+    pt = pbc(20, 3.0, pot=None)
+    pt["potentials"] = [{"kind": "poschTeller2b", "sets": [0, 0], "R0": 0.8}]
+    out["posch_teller2b_N20"] = (pt, rng.uniform(-3, 3, size=(6, 60)))
+    out["three_body_N32"] = (three_body(32), rng.uniform(-2.5, 2.5, size=(4, 96)))
+    out["three_body_hs_N32"] = (three_body(32, hs=0.9), rng.uniform(-2.5, 2.5, size=(8, 96)))
     return out
 
 

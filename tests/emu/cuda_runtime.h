@@ -133,6 +133,12 @@ static inline double __dadd_rn(double a, double b)
   volatile double r = a + b;
   return r;
 }
+static inline long long __double_as_longlong(double d)
+{
+  long long u;
+  std::memcpy(&u, &d, 8);
+  return u;
+}
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline float emu_log2f(float x) { return log2f(x); }
 static inline void emu_sincosf(float x, float *s, float *c)
@@ -154,7 +160,7 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2
 typedef struct emu_stream *cudaStream_t;
 typedef struct emu_event *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 struct cudaFuncAttributes { int numRegs = 0; size_t sharedSizeBytes = 0; int maxThreadsPerBlock = 1024; };
@@ -180,6 +186,10 @@ cudaError_t cudaMemcpyAsync(void *, const void *, size_t, cudaMemcpyKind, cudaSt
 cudaError_t cudaMemset(void *, int, size_t);
 cudaError_t cudaMemsetAsync(void *, int, size_t, cudaStream_t = nullptr);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *, unsigned);
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *, unsigned, int);
+cudaError_t cudaDeviceGetStreamPriorityRange(int *, int *);
+cudaError_t cudaHostAlloc(void **, size_t, unsigned);
+cudaError_t cudaFreeHost(void *);
 cudaError_t cudaStreamDestroy(cudaStream_t);
 cudaError_t cudaStreamSynchronize(cudaStream_t);
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0);

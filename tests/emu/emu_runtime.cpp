@@ -152,6 +152,15 @@ cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cu
 cudaError_t cudaMemset(void *d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new emu_stream{0}; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = new emu_stream{0}; return cudaSuccess; }
+cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi)
+{
+  if (lo) *lo = 0;
+  if (hi) *hi = 0;
+  return cudaSuccess;
+}
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return (*p = std::malloc(n)) ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }

@@ -19,17 +19,42 @@ lib = capi.load()
 buf = C.create_string_buffer(128)
 assert lib.qmc_comm_unique_id(buf) == 0
 uid = buf.raw
+assert lib.qmc_comm_unique_id(buf) == 0
+uid2 = buf.raw
 out = [None] * NR
 err = []
 
 def run(r):
     try:
-        s = System.from_input(cfg, device=0, comm=(uid, r, NR))
         rng = np.random.default_rng(100 + r)
         L = np.asarray(cfg["lBox"])
         n0 = WPR + (r * 5) % 7 - 3          # unequal start
         R = (rng.uniform(-0.5, 0.5, size=(n0, 3, N)) * L[None, :, None]).reshape(n0, -1)
+        # ---- (A) in-step migration (one step late, dead band 0 = the reference's behaviour): every step must move exactly
+        # the global population — a lost or duplicated walker shows up in the all-reduced move counter
+        s = System.from_input(cfg, device=0, comm=(uid, r, NR))
         s.upload(R)
+        assert lib.qmc_set_migration(s.ctx, 1, 0.0) == 0
+        moves_ok = True
+        for k in range(8):
+            gpop = s.info("global_population")
+            s.step(1, 1)
+            bk = s.block_results()
+            if not (bk["n_moves"] == gpop and bk["steps_done"] == 1):
+                print("rank", r, "step", k, "moved", bk["n_moves"], "global population", gpop, "steps", bk["steps_done"])
+                moves_ok = False
+        Rm, Em = s.download(with_energy=True)
+        ev = s.eval(Rm)          # the payload that travelled is intact: E stored with a walker = E_L of its configuration
+        if not np.allclose(ev["E"], Em, rtol=1e-9, atol=1e-9):
+            print("rank", r, "E mismatch", np.abs(ev["E"] - Em).max())
+            moves_ok = False
+        mig = (s.info("migration_events"), s.info("migrated_out"), s.info("migrated_in"))
+        gpop_end, pop_end = s.info("global_population"), len(Rm)
+        s.close()
+        # ---- (B) the explicit call (qmc_rebalance) with the in-step migration switched off
+        s = System.from_input(cfg, device=0, comm=(uid2, r, NR))
+        s.upload(R)
+        assert lib.qmc_set_migration(s.ctx, 1, 1e9) == 0
         s.step(10, 1)
         b0 = s.block_results()
         Rb, Eb = s.download(with_energy=True)
@@ -37,7 +62,11 @@ def run(r):
         Ra, Ea = s.download(with_energy=True)
         s.step(10, 1)
         b1 = s.block_results()
-        out[r] = dict(b0=b0, b1=b1, Rb=Rb, Ra=Ra, Eb=Eb, Ea=Ea, moved=moved, wpw=s.info("warps_per_walker"))
+        if s.info("migration_events") != (1 if moved else 0):
+            print("rank", r, "explicit phase: migration events", s.info("migration_events"), "moved", moved)
+            moves_ok = False
+        out[r] = dict(b0=b0, b1=b1, Rb=Rb, Ra=Ra, Eb=Eb, Ea=Ea, moved=moved, wpw=s.info("warps_per_walker"), moves_ok=moves_ok, mig=mig,
+                      n0=n0, gpop_end=gpop_end, pop_end=pop_end)
         s.close()
     except Exception as e:
         import traceback; traceback.print_exc()
@@ -64,6 +93,9 @@ ok &= max(pops) - min(pops) <= 1 and sum(pops) == len(before)                   
 ok &= sum(o["moved"] for o in out) == 0
 for k in ("energy_shift", "n_moves", "n_accepted", "energy_sum", "energy_count"):  # block results are global on every rank
     ok &= len({o["b0"][k] for o in out}) == 1 and len({o["b1"][k] for o in out}) == 1
-ok &= out[0]["b0"]["n_moves"] == len(before) * 0 + out[0]["b0"]["n_moves"]
+ok &= all(o["moves_ok"] for o in out)                                              # every step moved the whole global population once
+print("in-step migration (events, out, in) per rank:", [o["mig"] for o in out], "initial", [o["n0"] for o in out])
+ok &= sum(o["mig"][1] for o in out) == sum(o["mig"][2] for o in out) > 0           # walkers left = walkers arrived, and some did
+ok &= sum(o["pop_end"] for o in out) == out[0]["gpop_end"]                          # the ranks' populations add up to the all-reduced one
 print("OK" if ok else "FAILED")
 sys.exit(0 if ok else 1)

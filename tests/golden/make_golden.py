@@ -88,6 +88,19 @@ def main():
         if "--force-energy" in sys.argv:
             force_energy(ref)
         return
+    if "--append-eval" in sys.argv:
+        # add the cases named after the flag to eval_cases.npz without touching the fixtures that are already pinned
+        names = sys.argv[sys.argv.index("--append-eval") + 1:]
+        old = dict(np.load(os.path.join(HERE, "eval_cases.npz")))
+        for name in names:
+            cfg, R = cases.eval_cases()[name]
+            r = ref.eval(cfg, R)
+            old[name + "/R"] = R
+            for k, v in r.items():
+                old[name + "/" + k] = v
+            print(name, {k: np.asarray(v).shape for k, v in r.items()})
+        np.savez_compressed(os.path.join(HERE, "eval_cases.npz"), **old)
+        return
     rng = np.random.default_rng(424242)
     out = {}
     for name, (cfg, R) in cases.eval_cases().items():

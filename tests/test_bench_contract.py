@@ -19,7 +19,8 @@ def test_reference_arm_json_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "walker-moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["config"]["workload"].startswith("config2")
+    assert line["config"]["workload"].startswith("config5")          # the configuration the north-star targets are quoted on
+    assert line["config"]["cpu_walkers_per_process"] >= 8 and line["config"]["dmc_steps_per_bench_step"] >= 1
 
 
 def test_workloads_follow_the_baseline_configs():

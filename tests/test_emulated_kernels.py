@@ -92,10 +92,9 @@ def test_forward_walking_records_migrate_between_emulated_ranks(emu_lib, nranks,
 
 
 @pytest.mark.skipif(os.environ.get("QMC4_TEST_EMULATED_SLOW") != "1", reason="minutes of CPU: set QMC4_TEST_EMULATED_SLOW=1")
-def test_experimental_pipeline2_bitwise_on_emulated_kernels(emu_lib):
+def test_pipeline2_bitwise_on_emulated_kernels(emu_lib):
     env = _env(emu_lib)
-    env["QMC4_TEST_EXPERIMENTAL"] = "1"
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_experimental_pipeline2.py"), "-q",
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_pipeline2.py"), "-q",
                         "-m", "gpu", "-p", "no:cacheprovider"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=3000)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
@@ -152,7 +151,7 @@ def test_kernels_under_sanitizers(tmp_path, san):
     for name, cfg in inputs.items():
         run(name, cfg)
     run("two_gpus_record_migration", inputs["fw_pair_superfluid"], "--gpus", "2", QMC4_EMU_DEVICES="2")
-    run("pipeline2", inputs["structure_factor"], QMC4_PIPELINE="2")
+    run("pipeline1", inputs["structure_factor"], QMC4_PIPELINE="1")
 
 
 def _run_host(tmp_path, cfg, *extra, devices=1):

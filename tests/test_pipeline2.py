@@ -1,7 +1,7 @@
-"""Opt-in GPU tests of the EXPERIMENTAL step pipeline (QMC4_PIPELINE=2, qmc4_b200/csrc/kernels_v2.cu).
-Skipped unless QMC4_TEST_EXPERIMENTAL=1: the pipeline was written after the round-1 GPU budget was spent
-and has not run on hardware yet.  The contract it must meet: trajectories bitwise identical to pipeline 1
-(same Philox draws, same formulas) and identical fixed-point g(r)."""
+"""GPU tests of the production step pipeline (pipeline 2, qmc4_b200/csrc/kernels_v2.cu: move -> scan -> estimators, the
+collective and the migration on a second stream) against the fused pipeline 1 of kernels.cu (QMC4_PIPELINE=1), which the
+traced-step parity tests pin on the oracle: trajectories must be bitwise identical (same Philox draws, same formulas) and
+the fixed-point g(r) identical."""
 import os
 
 import numpy as np
@@ -9,13 +9,15 @@ import pytest
 
 import cases
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("QMC4_TEST_EXPERIMENTAL") != "1", reason="experimental pipeline: opt-in")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _run(pipeline, cfg, R, steps):
     from qmc4_b200.system import System
-    os.environ["QMC4_PIPELINE"] = str(pipeline)
+    if pipeline == 1:
+        os.environ["QMC4_PIPELINE"] = "1"
+    else:
+        os.environ.pop("QMC4_PIPELINE", None)       # pipeline 2 is the default
     try:
         s = System.from_input(cfg)
         assert s.info("pipeline") == pipeline
