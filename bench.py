@@ -321,7 +321,7 @@ def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, s
     config = describe(cfgno, cfg, wpg, ngpu, args.scaling, equil, dmc_steps, flushed=not args.no_flush)
     s = parallel.make_comm(lambda comm: System.from_input(cfg, device=local, comm=comm))
     if args.migrate_every or args.migrate_band is not None:
-        s.set_migration(args.migrate_every or 1, 0.005 if args.migrate_band is None else args.migrate_band)
+        s.set_migration(args.migrate_every or 1, 0.01 if args.migrate_band is None else args.migrate_band)
     dofs = s.dofs
     s.upload(initial_walkers(cfg, wpg, 1000 + rank))
 
@@ -332,7 +332,7 @@ def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, s
         torch.cuda.synchronize()
 
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    sampler = ClockSampler(local) if (rank == 0 and primary) else None
+    sampler = ClockSampler(local) if (rank == 0 and primary and not os.environ.get("QMC4_BENCH_NO_SAMPLER")) else None
     m = measure(s, cfg, cfgno, steps, warmup, dmc_steps, equil, flush, barrier, world, rank, torch, dist, sampler)
     out = {"config": config, "m": m, "cfg": cfg}
 
@@ -360,7 +360,31 @@ def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, s
                                       "walkers_in": float(mig[2].item()), "every": m["migration"]["every"], "band": m["migration"]["band"]},
                 "explicit_rebalance": {"walkers_moved": float(mv.item()) / 2, "multiset_fingerprint_before": int(ck0.item()) % (1 << 52),
                                        "multiset_fingerprint_after": int(ck1.item()) % (1 << 52)}}
-            out["conservation"]["ok"] = bool(out["conservation"]["sum_of_rank_populations"] == out["conservation"]["all_reduced_population"]
+            # frozen-population check of the IN-STEP migration: with timeStep = 1e-300 a move changes nothing in fp64 and every
+            # walker has exactly one descendant, so only the migration moves walkers (unequal start, dead band 0): the global
+            # multiset fingerprint must not change while the populations equalise
+            sz = parallel.make_comm(lambda comm: System.from_input(dict(cfg, timeStep=1e-300), device=local, comm=comm))
+            sz.set_migration(1, 0.0)
+            nz = max(8, min(wpg, 2048) - 37 * rank)
+            sz.upload(initial_walkers(cfg, nz, 5000 + rank))
+            sz.step(1, 1)
+            fz0 = torch.tensor([int(sz.info("population_checksum"))], dtype=torch.int64, device="cuda")
+            dist.all_reduce(fz0)
+            sz.step(4, 1)
+            fz1 = torch.tensor([int(sz.info("population_checksum"))], dtype=torch.int64, device="cuda")
+            dist.all_reduce(fz1)
+            pz = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(pz, torch.tensor([sz.block_results()["population"]], dtype=torch.float64, device="cuda"))
+            mz = torch.tensor([sz.info("migrated_out"), sz.info("migrated_in")], dtype=torch.float64, device="cuda")
+            dist.all_reduce(mz)
+            sz.close()
+            pz = [float(p.item()) for p in pz]
+            out["conservation"]["frozen_population_in_step"] = {
+                "start_populations": [max(8, min(wpg, 2048) - 37 * r) for r in range(world)], "end_populations": pz,
+                "walkers_out": float(mz[0].item()), "walkers_in": float(mz[1].item()),
+                "multiset_fingerprint_before": int(fz0.item()) % (1 << 52), "multiset_fingerprint_after": int(fz1.item()) % (1 << 52)}
+            fz_ok = (int(fz0.item()) % (1 << 52) == int(fz1.item()) % (1 << 52) and max(pz) - min(pz) <= 1 and mz[0].item() == mz[1].item() > 0)
+            out["conservation"]["ok"] = fz_ok and bool(out["conservation"]["sum_of_rank_populations"] == out["conservation"]["all_reduced_population"]
                                              and mig[1].item() == mig[2].item()
                                              and out["conservation"]["explicit_rebalance"]["multiset_fingerprint_before"]
                                              == out["conservation"]["explicit_rebalance"]["multiset_fingerprint_after"])

@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <time.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -142,10 +143,15 @@ struct qmc_ctx {
   double *h_sums = nullptr;         // pinned copy of Ctl::gsum after the last all-reduce: what the migration planner reads
   bool pops_pending = false;        // h_sums holds populations the planner has not looked at yet
   int mig_every = 1;                // plan a migration every mig_every steps ...
-  double mig_band = 0.005;          // ... if max-min population exceeds this fraction of the mean (dead band), min 1 walker
+  double mig_band = 0.01;           // ... if max-min population exceeds this fraction of the mean (dead band), min 1 walker
   long mig_phase = 0, mig_events = 0, mig_out = 0, mig_in = 0;
   int slab_walkers = 0;             // walkers one migration slab holds (bounds a step's transfers)
+  bool p2p_connected = false;       // every directed pair of ranks has exchanged a message (NCCL connects lazily: ~140 ms per pair)
   unsigned long long *d_checksum = nullptr;
+  // QMC4_TRACE=n: device/host timeline of the first n steps of every qmc_step call, printed to stderr (diagnostics)
+  struct StepTrace { cudaEvent_t m0, m1, s1, e1, a1; double h_enter, h_wait0, h_wait1, h_exit; int mig; };
+  std::vector<StepTrace> trace;
+  int trace_n = 0, trace_used = 0;
   int est_occ = 4, est_grid = 0;      // estimator kernel of pipeline 2: resident CTAs per SM it is compiled for, its grid
   double *e_old = nullptr;
   // forward walking (kernels_fw.cu; correlationEstimator.cpp): ring of per-slot histogram rows + ancestor links
@@ -865,8 +871,23 @@ void plan_migration(qmc_ctx *c, std::vector<int> &src, std::vector<int> &amt, in
   n_recv = amt[c->rank];
 }
 
+double host_now_ms()
+{
+  timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+
 int one_step_v2(qmc_ctx *c, int accumulate)
 { /* move(k) || { all-reduce(k-1), migration(k-1) }  ->  [move(k) on the arrivals]  ->  scan(k)  ->  { all-reduce(k) } || estimators(k) || move(k+1) */
+  qmc_ctx::StepTrace *T = (c->trace_used < c->trace_n) ? &c->trace[c->trace_used++] : nullptr;
+  if (T)
+    {
+      T->h_enter = host_now_ms();
+      T->h_wait0 = T->h_wait1 = 0;
+      T->mig = 0;
+      CK(cudaEventRecord(T->m0, c->stream));
+    }
   StepArgs a = make_step_args(c, accumulate);
   a.hist = nullptr;
   a.flags = c->flags;
@@ -877,13 +898,15 @@ int one_step_v2(qmc_ctx *c, int accumulate)
   if (timed) CK(cudaEventRecord(c->pev0[c->pev_used], c->stream));
   CK(launch_propagate_v2(c->ksel, c->cfg, c->cfg.grid, c->stream, c->plan, c->dmc, a, c->e_old));
   if (timed) CK(cudaEventRecord(c->pev1[c->pev_used++], c->stream));
+  if (T) CK(cudaEventRecord(T->m1, c->stream));
   c->launches += 1;
-  if (c->nranks > 1 && c->dmc.branching_on && c->pops_pending)
+  if (c->nranks > 1 && c->dmc.branching_on && c->pops_pending && ++c->mig_phase % c->mig_every == 0)
     { /* one step late, like dmcDriver::isend (dmcDriver.cpp:112,150-157): while the move kernel runs, the host reads the
          populations the previous step's all-reduce delivered and posts the transfers on the communication stream */
+      if (T) T->h_wait0 = host_now_ms();
       if (c->ar_pending) CK(cudaEventSynchronize(c->ev_ar));
+      if (T) T->h_wait1 = host_now_ms();
       c->pops_pending = false;
-      if (++c->mig_phase % c->mig_every == 0)
         {
           std::vector<int> src, amt;
           int n_send = 0, n_recv = 0;
@@ -902,13 +925,13 @@ int one_step_v2(qmc_ctx *c, int accumulate)
                   }
               if (n_recv > 0) NK(g_nccl.Recv(c->slab_recv, (size_t)n_recv * wsz, NCCL_FLOAT64, src[c->rank], c->comm, c->comm_stream));
               NK(g_nccl.GroupEnd());
-              CK(launch_unpack_append(c->comm_stream, a.in, c->parent, c->ctl, (int)dofs, n_recv, c->slab_recv));
+              CK(launch_unpack_append(c->comm_stream, a.in, c->parent, c->ctl, (int)dofs, n_send, n_recv, c->slab_recv));
               CK(cudaEventRecord(c->ev_mig, c->comm_stream));
               CK(cudaStreamWaitEvent(c->stream, c->ev_mig, 0));
               if (n_recv > 0)
                 { /* late arrivals are advanced within the same step (ptools.cpp:379-394, dmcDriver.cpp:133-136) */
                   StepArgs t = a;
-                  t.first = -1;
+                  t.first = -1 - n_send;       /* appended behind the walkers that stay */
                   t.count = n_recv;
                   const int g = std::max(1, std::min(c->cfg.grid, (n_recv + c->cfg.groups_per_cta - 1) / c->cfg.groups_per_cta));
                   CK(launch_propagate_v2(c->ksel, c->cfg, g, c->stream, c->plan, c->dmc, t, c->e_old));
@@ -917,6 +940,7 @@ int one_step_v2(qmc_ctx *c, int accumulate)
               a.n_adjust = n_recv - n_send;
               c->launches += (n_send > 0) + (n_recv > 0);
               c->mig_events += 1;
+              if (T) T->mig = n_send + n_recv;
               c->mig_out += n_send;
               c->mig_in += n_recv;
             }
@@ -924,6 +948,7 @@ int one_step_v2(qmc_ctx *c, int accumulate)
     }
   if (c->ar_pending) CK(cudaStreamWaitEvent(c->stream, c->ev_ar, 0));        /* scan needs E_T of the previous population */
   CK(launch_scan_v2(c->stream, c->dmc, a, c->e_old, c->nranks > 1));
+  if (T) CK(cudaEventRecord(T->s1, c->stream));
   c->launches += 1;
   c->cur ^= 1;
   if (c->nranks > 1)
@@ -933,15 +958,42 @@ int one_step_v2(qmc_ctx *c, int accumulate)
       NK(g_nccl.AllReduce(c->ctl->lsum, c->ctl->gsum, NSUM, NCCL_FLOAT64, NCCL_SUM, c->comm, c->comm_stream));
       CK(cudaMemcpyAsync(c->h_sums, c->ctl->gsum, sizeof(double) * NSUM, cudaMemcpyDeviceToHost, c->comm_stream));
       CK(cudaEventRecord(c->ev_ar, c->comm_stream));
+      if (T) CK(cudaEventRecord(T->a1, c->comm_stream));
       c->ar_pending = true;
       c->pops_pending = true;
     }
+  else if (T) CK(cudaEventRecord(T->a1, c->stream));
   if (accumulate && c->has_hist)
     {
       CK(launch_estimators(c->cfg, c->stream, c->plan, c->buf[c->cur], c->parent, c->ctl, c->hist, c->est_occ, c->est_grid));
       c->launches += 1;
     }
+  if (T)
+    {
+      CK(cudaEventRecord(T->e1, c->stream));
+      T->h_exit = host_now_ms();
+    }
   return 0;
+}
+
+void dump_trace(qmc_ctx *c, double h0)
+{
+  if (c->trace_used == 0) return;
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+  fprintf(stderr, "[qmc4 trace rank %d] step: device ms since call start {move0 move1 scan1 est1 ar1} | host ms {enter wait0 wait1 exit} mig\n", c->rank);
+  for (int i = 0; i < c->trace_used; ++i)
+    {
+      qmc_ctx::StepTrace &t = c->trace[i];
+      float m0 = 0, m1 = 0, s1 = 0, e1 = 0, a1 = 0;
+      cudaEventElapsedTime(&m0, c->ev0, t.m0);
+      cudaEventElapsedTime(&m1, c->ev0, t.m1);
+      cudaEventElapsedTime(&s1, c->ev0, t.s1);
+      cudaEventElapsedTime(&e1, c->ev0, t.e1);
+      cudaEventElapsedTime(&a1, c->ev0, t.a1);
+      fprintf(stderr, "[qmc4 trace rank %d] %3d: %8.3f %8.3f %8.3f %8.3f %8.3f | %8.3f %8.3f %8.3f %8.3f  %d\n", c->rank, i, m0, m1, s1, e1, a1,
+              t.h_enter - h0, t.h_wait0 ? t.h_wait0 - h0 : 0.0, t.h_wait1 ? t.h_wait1 - h0 : 0.0, t.h_exit - h0, t.mig);
+    }
+  c->trace_used = 0;
 }
 
 int force_energy_pass(qmc_ctx *c);
@@ -1115,6 +1167,19 @@ int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, co
     if ((e = cudaHostAlloc((void **)&c->h_sums, sizeof(double) * NSUM, cudaHostAllocDefault)) != cudaSuccess) return bail(cudaGetErrorString(e));
     memset(c->h_sums, 0, sizeof(double) * NSUM);
   }
+  if (const char *v = getenv("QMC4_TRACE"))
+    {
+      c->trace_n = std::max(0, std::min(512, atoi(v)));
+      c->trace.resize(c->trace_n);
+      for (auto &t : c->trace)
+        {
+          cudaEventCreate(&t.m0);
+          cudaEventCreate(&t.m1);
+          cudaEventCreate(&t.s1);
+          cudaEventCreate(&t.e1);
+          cudaEventCreate(&t.a1);
+        }
+    }
   if (const char *v = getenv("QMC4_MIGRATE_EVERY"))
     c->mig_every = std::max(1, atoi(v));
   if (const char *v = getenv("QMC4_MIGRATE_BAND"))
@@ -1626,6 +1691,19 @@ int qmc_upload_walkers(qmc_ctx *c, const double *R, int64_t nW)
   CK(launch_scan(c->stream, c->dmc, a, 0, c->nranks > 1, 1));
   c->launches += 2;
   if (allreduce_sums(c)) return 1;
+  if (c->nranks > 1 && !c->p2p_connected)
+    { /* NCCL sets up point-to-point connections lazily, one directed pair at a time (~140 ms each on NVLink, measured): a
+         migration inside a step must never pay that, so every pair exchanges one double here, once, in a single group */
+      NK(g_nccl.GroupStart());
+      for (int r = 0; r < c->nranks; ++r)
+        if (r != c->rank)
+          {
+            NK(g_nccl.Send(c->slab_send + r, 1, NCCL_FLOAT64, r, c->comm, c->stream));
+            NK(g_nccl.Recv(c->slab_recv + r, 1, NCCL_FLOAT64, r, c->comm, c->stream));
+          }
+      NK(g_nccl.GroupEnd());
+      c->p2p_connected = true;
+    }
   Ctl h;
   CK(cudaMemcpyAsync(&h, c->ctl, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1674,6 +1752,8 @@ int qmc_step(qmc_ctx *c, int nSteps, int sampleEvery)
   if (c->planning_only) return fail(c, "planning-only context (device -1): no CUDA device, no compute (there is no CPU fallback)");
   cudaSetDevice(c->device);
   if (sampleEvery < 1) sampleEvery = 1;
+  const double h0 = c->trace_n ? host_now_ms() : 0.0;
+  c->trace_used = 0;
   CK(cudaEventRecord(c->ev0, c->stream));
   for (int k = 0; k < nSteps; ++k)
     {
@@ -1686,6 +1766,7 @@ int qmc_step(qmc_ctx *c, int nSteps, int sampleEvery)
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->device_ms += ms;
+  if (c->trace_n) dump_trace(c, h0);
   return resolve_kernel_timers(c);
 }
 
@@ -2152,7 +2233,7 @@ int qmc_rebalance(qmc_ctx *c, int64_t *moved)
   n_cur -= n_send;
   if (n_recv > 0)
     { // received walkers land in free physical slots [n_prev, n_prev+n_recv) and are appended to the population
-      if (launch_unpack_append(c->stream, c->buf[c->cur], c->parent, c->ctl, (int)dofs, n_recv, c->slab_recv) != cudaSuccess)
+      if (launch_unpack_append(c->stream, c->buf[c->cur], c->parent, c->ctl, (int)dofs, n_send, n_recv, c->slab_recv) != cudaSuccess)
         return fatal("rebalance: unpack kernel launch failed");
       CK(cudaStreamSynchronize(c->stream));
       n_cur += n_recv;

@@ -66,7 +66,7 @@ struct StepArgs {
   TraceDev trace;
   // pipeline 2 (kernels_v2.cu)
   int *flags;                  // [cap] bit 0: move accepted (the scan counts the Metropolis statistics from these)
-  int first, count;            // move kernel: walkers [first, first+count); count < 0: [0, ctl->n_cur).  first < 0: first = ctl->n_cur
+  int first, count;            // move kernel: walkers [first, first+count); count < 0: [0, ctl->n_cur).  first = -1 - d: ctl->n_cur - d
   int n_adjust;                // scan: population moved this step = ctl->n_cur + n_adjust (arrivals - departures of the migration)
 };
 
@@ -112,7 +112,8 @@ cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, int grid, cudaSt
                                 const StepArgs &a, double *e_old);
 cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int multi_rank);
 cudaError_t launch_pack_tail(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, int dofs, int n_send, double *slab);
-cudaError_t launch_unpack_append(cudaStream_t st, const WalkerBuf &buf, int *parent, const Ctl *ctl, int dofs, int n_recv, const double *slab);
+cudaError_t launch_unpack_append(cudaStream_t st, const WalkerBuf &buf, int *parent, const Ctl *ctl, int dofs, int n_send, int n_recv,
+                                 const double *slab);
 cudaError_t launch_population_checksum(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, unsigned long long *out);
 cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const WalkerBuf &buf, const int *parent,
                               const Ctl *ctl, double *hist, int occ, int grid);

@@ -33,7 +33,7 @@ move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams
   const int dofs = plan.dofs;
   const Ctl *ctl = a.ctl;
   /* walkers [j0, j1): the whole population, or the walkers that arrived by migration during this step */
-  const int j0 = a.count < 0 ? 0 : (a.first < 0 ? ctl->n_cur : a.first);
+  const int j0 = a.count < 0 ? 0 : (a.first < 0 ? ctl->n_cur + a.first + 1 : a.first);      /* first = -1 - d: n_cur - d */
   const int j1 = a.count < 0 ? ctl->n_cur : j0 + a.count;
   const unsigned long long step = ctl->step;
   const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
@@ -318,10 +318,11 @@ __global__ void pack_tail_kernel(WalkerBuf buf, const int *parent, const Ctl *ct
         }
     }
 }
-// arrivals land in the free physical slots [n_prev, n_prev + n_recv) and are appended to the population at [n_cur, n_cur + n_recv)
-__global__ void unpack_append_kernel(WalkerBuf buf, int *parent, const Ctl *ctl, int dofs, int n_recv, const double *slab)
+// arrivals land in the free physical slots [n_prev, n_prev + n_recv) and are appended to what remains of the population after
+// this rank's own departures: a rank the plan first drains and then tops up both sends and receives (ptools.cpp:93-161)
+__global__ void unpack_append_kernel(WalkerBuf buf, int *parent, const Ctl *ctl, int dofs, int n_send, int n_recv, const double *slab)
 {
-  const int slot0 = ctl->n_prev, idx0 = ctl->n_cur;
+  const int slot0 = ctl->n_prev, idx0 = ctl->n_cur - n_send;
   for (int w = blockIdx.x; w < n_recv; w += gridDim.x)
     {
       const double *src = slab + (size_t)w * (2 * dofs + 2);
@@ -449,10 +450,11 @@ cudaError_t launch_pack_tail(cudaStream_t st, const WalkerBuf &buf, const int *p
   QMC_LAUNCH(pack_tail_kernel, n_send < 512 ? n_send : 512, 128, 0, st, buf, parent, ctl, dofs, n_send, slab);
   return cudaGetLastError();
 }
-cudaError_t launch_unpack_append(cudaStream_t st, const WalkerBuf &buf, int *parent, const Ctl *ctl, int dofs, int n_recv, const double *slab)
+cudaError_t launch_unpack_append(cudaStream_t st, const WalkerBuf &buf, int *parent, const Ctl *ctl, int dofs, int n_send, int n_recv,
+                                 const double *slab)
 {
   if (n_recv <= 0) return cudaSuccess;
-  QMC_LAUNCH(unpack_append_kernel, n_recv < 512 ? n_recv : 512, 128, 0, st, buf, parent, ctl, dofs, n_recv, slab);
+  QMC_LAUNCH(unpack_append_kernel, n_recv < 512 ? n_recv : 512, 128, 0, st, buf, parent, ctl, dofs, n_send, n_recv, slab);
   return cudaGetLastError();
 }
 cudaError_t launch_population_checksum(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, unsigned long long *out)

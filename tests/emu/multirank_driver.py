@@ -21,6 +21,8 @@ assert lib.qmc_comm_unique_id(buf) == 0
 uid = buf.raw
 assert lib.qmc_comm_unique_id(buf) == 0
 uid2 = buf.raw
+assert lib.qmc_comm_unique_id(buf) == 0
+uid3 = buf.raw
 out = [None] * NR
 err = []
 
@@ -51,6 +53,16 @@ def run(r):
         mig = (s.info("migration_events"), s.info("migrated_out"), s.info("migrated_in"))
         gpop_end, pop_end = s.info("global_population"), len(Rm)
         s.close()
+        # ---- (A') exact identity test of the in-step path: with timeStep = 1e-300 a move changes nothing in fp64 and every
+        # walker has exactly one descendant, so the population is frozen and only the migration moves walkers between the
+        # ranks (some ranks both send and receive in the alias plan): the global multiset must be preserved bit for bit
+        s = System.from_input(dict(cfg, timeStep=1e-300), device=0, comm=(uid3, r, NR))
+        s.upload(R)
+        assert lib.qmc_set_migration(s.ctx, 1, 0.0) == 0
+        s.step(3, 1)
+        Rz = s.download()
+        frozen = (R, Rz, s.info("migrated_out"), s.info("migrated_in"))
+        s.close()
         # ---- (B) the explicit call (qmc_rebalance) with the in-step migration switched off
         s = System.from_input(cfg, device=0, comm=(uid2, r, NR))
         s.upload(R)
@@ -66,7 +78,7 @@ def run(r):
             print("rank", r, "explicit phase: migration events", s.info("migration_events"), "moved", moved)
             moves_ok = False
         out[r] = dict(b0=b0, b1=b1, Rb=Rb, Ra=Ra, Eb=Eb, Ea=Ea, moved=moved, wpw=s.info("warps_per_walker"), moves_ok=moves_ok, mig=mig,
-                      n0=n0, gpop_end=gpop_end, pop_end=pop_end)
+                      n0=n0, gpop_end=gpop_end, pop_end=pop_end, frozen=frozen)
         s.close()
     except Exception as e:
         import traceback; traceback.print_exc()
@@ -97,5 +109,10 @@ ok &= all(o["moves_ok"] for o in out)                                           
 print("in-step migration (events, out, in) per rank:", [o["mig"] for o in out], "initial", [o["n0"] for o in out])
 ok &= sum(o["mig"][1] for o in out) == sum(o["mig"][2] for o in out) > 0           # walkers left = walkers arrived, and some did
 ok &= sum(o["pop_end"] for o in out) == out[0]["gpop_end"]                          # the ranks' populations add up to the all-reduced one
+fz0 = np.concatenate([o["frozen"][0] for o in out]); fz1 = np.concatenate([o["frozen"][1] for o in out])
+pz = [len(o["frozen"][1]) for o in out]
+print("frozen-population run: multiset preserved by the in-step migration:", np.array_equal(key(fz0), key(fz1)), "populations", pz,
+      "moved", sum(o["frozen"][2] for o in out))
+ok &= np.array_equal(key(fz0), key(fz1)) and max(pz) - min(pz) <= 1 and sum(o["frozen"][2] for o in out) == sum(o["frozen"][3] for o in out) > 0
 print("OK" if ok else "FAILED")
 sys.exit(0 if ok else 1)
