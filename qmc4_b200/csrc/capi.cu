@@ -148,6 +148,11 @@ struct qmc_ctx {
   int slab_walkers = 0;             // walkers one migration slab holds (bounds a step's transfers)
   bool p2p_connected = false;       // every directed pair of ranks has exchanged a message (NCCL connects lazily: ~140 ms per pair)
   unsigned long long *d_checksum = nullptr;
+  // the hot kernel of the one-species / one-pair-pass shapes (kernels_pair.cu) replaces the general move kernel when the plan allows
+  bool lean = false;
+  int lean_vk = V_NONE, lean_occ = 2;
+  LaunchCfg lean_cfg = {};
+  double *lean_tab = nullptr;       // 2^(j/256), j = 0..255 (device)
   // QMC4_TRACE=n: device/host timeline of the first n steps of every qmc_step call, printed to stderr (diagnostics)
   struct StepTrace { cudaEvent_t m0, m1, s1, e1, a1; double h_enter, h_wait0, h_wait1, h_exit; int mig; };
   std::vector<StepTrace> trace;
@@ -878,7 +883,7 @@ double host_now_ms()
   return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
 }
 
-int one_step_v2(qmc_ctx *c, int accumulate)
+int one_step_v2(qmc_ctx *c, int accumulate, const TraceDev *tr)
 { /* move(k) || { all-reduce(k-1), migration(k-1) }  ->  [move(k) on the arrivals]  ->  scan(k)  ->  { all-reduce(k) } || estimators(k) || move(k+1) */
   qmc_ctx::StepTrace *T = (c->trace_used < c->trace_n) ? &c->trace[c->trace_used++] : nullptr;
   if (T)
@@ -894,9 +899,11 @@ int one_step_v2(qmc_ctx *c, int accumulate)
   a.first = 0;
   a.count = -1;
   a.n_adjust = 0;
+  if (tr) a.trace = *tr;
   const bool timed = c->time_kernels && c->pev_used < qmc_ctx::NEV;
   if (timed) CK(cudaEventRecord(c->pev0[c->pev_used], c->stream));
-  CK(launch_propagate_v2(c->ksel, c->cfg, c->cfg.grid, c->stream, c->plan, c->dmc, a, c->e_old));
+  if (c->lean) CK(launch_pair_move(c->lean_vk, c->lean_occ, c->lean_cfg, c->lean_cfg.grid, c->stream, c->plan, c->dmc, c->lean_tab, a, c->e_old));
+  else CK(launch_propagate_v2(c->ksel, c->cfg, c->cfg.grid, c->stream, c->plan, c->dmc, a, c->e_old));
   if (timed) CK(cudaEventRecord(c->pev1[c->pev_used++], c->stream));
   if (T) CK(cudaEventRecord(T->m1, c->stream));
   c->launches += 1;
@@ -933,8 +940,10 @@ int one_step_v2(qmc_ctx *c, int accumulate)
                   StepArgs t = a;
                   t.first = -1 - n_send;       /* appended behind the walkers that stay */
                   t.count = n_recv;
-                  const int g = std::max(1, std::min(c->cfg.grid, (n_recv + c->cfg.groups_per_cta - 1) / c->cfg.groups_per_cta));
-                  CK(launch_propagate_v2(c->ksel, c->cfg, g, c->stream, c->plan, c->dmc, t, c->e_old));
+                  const LaunchCfg &K = c->lean ? c->lean_cfg : c->cfg;
+                  const int g = std::max(1, std::min(K.grid, (n_recv + K.groups_per_cta - 1) / K.groups_per_cta));
+                  if (c->lean) CK(launch_pair_move(c->lean_vk, c->lean_occ, K, g, c->stream, c->plan, c->dmc, c->lean_tab, t, c->e_old));
+                  else CK(launch_propagate_v2(c->ksel, c->cfg, g, c->stream, c->plan, c->dmc, t, c->e_old));
                   c->launches += 1;
                 }
               a.n_adjust = n_recv - n_send;
@@ -1000,7 +1009,7 @@ int force_energy_pass(qmc_ctx *c);
 
 int one_step(qmc_ctx *c, int accumulate, const TraceDev *tr)
 {
-  if (c->pipeline == 2 && !tr) return one_step_v2(c, accumulate);
+  if (c->pipeline == 2) return one_step_v2(c, accumulate, tr);
   StepArgs a = make_step_args(c, accumulate);
   if (tr) a.trace = *tr;
   const bool hist = accumulate && c->has_hist;
@@ -1155,6 +1164,7 @@ int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, co
   if (const char *pv = getenv("QMC4_PIPELINE"))
     if (atoi(pv) == 1) c->pipeline = 1;
   if ((e = configure_kernels_v2(c->max_smem)) != cudaSuccess) return bail(std::string("kernel image (v2): ") + cudaGetErrorString(e));
+  if ((e = configure_kernels_pair(c->max_smem)) != cudaSuccess) return bail(std::string("kernel image (pair): ") + cudaGetErrorString(e));
   {
     /* the communication stream outranks the compute stream: the 144-byte all-reduce of step k is enqueued before the
        estimator / move kernels that follow the scan, and its CTA is placed first */
@@ -1206,6 +1216,7 @@ void qmc_destroy(qmc_ctx *c)
   cudaFree(c->e_old);
   cudaFree(c->flags);
   cudaFree(c->d_checksum);
+  cudaFree(c->lean_tab);
   if (c->h_sums) cudaFreeHost(c->h_sums);
   if (c->ev_scan) cudaEventDestroy(c->ev_scan);
   if (c->ev_ar) cudaEventDestroy(c->ev_ar);
@@ -1461,6 +1472,43 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
     }
   CK(cudaMalloc(&c->d_checksum, 8));
   c->cfg.grid = grid_for(c, capacity);
+  {
+    const Plan &P = c->plan;
+    const char *le = getenv("QMC4_LEAN");
+    c->lean = c->pipeline == 2 && !(le && atoi(le) == 0) && P.nSpecies == 1 && P.n1b == 0 && P.n2b == 1 && P.n3b == 0 &&
+              P.p2[0].setA == 0 && P.p2[0].setB == 0 && P.p2[0].J.kind == J_GAUSSGAUSS && (P.p2[0].vkind == V_STEP || P.p2[0].vkind == V_NONE);
+    if (c->lean)
+      {
+        c->lean_vk = P.p2[0].vkind;
+        if (const char *o = getenv("QMC4_LEAN_OCC")) c->lean_occ = atoi(o) >= 3 ? 3 : 2;
+        LaunchCfg &L = c->lean_cfg;
+        L.block = 256;
+        L.nwarps_per_group = pair_warps_per_walker(P.N[0]);
+        if (const char *w = getenv("QMC4_LEAN_WPW"))
+          {
+            const int v = atoi(w);
+            if (v == 1 || v == 2 || v == 4 || v == 8) L.nwarps_per_group = v;
+          }
+        L.groups_per_cta = 8 / L.nwarps_per_group;
+        L.smem = pair_group_bytes(P, L.nwarps_per_group) * L.groups_per_cta + pair_cta_extra_bytes();
+        if ((int)L.smem > c->max_smem) c->lean = false;
+        else
+          {
+            int per_sm = std::max(1, std::min(pair_move_occupancy(c->lean_vk, c->lean_occ, L.smem), 2048 / L.block));
+            if (const char *e2 = getenv("QMC4_CTAS_PER_SM"))
+              {
+                const int v = atoi(e2);
+                if (v >= 1 && v <= 8) per_sm = v;
+              }
+            const int64_t want = (capacity + L.groups_per_cta - 1) / L.groups_per_cta;
+            L.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sms * per_sm));
+            double tab[256];
+            pair_exp_table(tab);
+            CK(cudaMalloc(&c->lean_tab, sizeof tab));
+            CK(cudaMemcpy(c->lean_tab, tab, sizeof tab, cudaMemcpyHostToDevice));
+          }
+      }
+  }
   c->n_partials = c->cfg.grid * c->cfg.groups_per_cta;
   CK(cudaMalloc(&c->partials, (size_t)c->n_partials * 2 * 8));
   CK(cudaMemset(c->partials, 0, (size_t)c->n_partials * 2 * 8));
@@ -2354,14 +2402,17 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "log_up") *value = c->dmc.log_up;
   else if (k == "log_down") *value = c->dmc.log_down;
   else if (k == "capacity") *value = (double)c->cap;
-  else if (k == "grid") *value = c->cfg.grid;
+  else if (k == "grid") *value = c->lean ? c->lean_cfg.grid : c->cfg.grid;
   else if (k == "estimator_grid") *value = c->est_grid;
   else if (k == "estimator_occupancy_target") *value = c->est_occ;
   else if (k == "block") *value = c->cfg.block;
-  else if (k == "smem_bytes") *value = (double)c->cfg.smem;
-  else if (k == "warps_per_walker") *value = c->cfg.nwarps_per_group;
+  else if (k == "smem_bytes") *value = (double)(c->lean ? c->lean_cfg.smem : c->cfg.smem);
+  else if (k == "warps_per_walker") *value = c->cfg.nwarps_per_group;      /* general kernels (evaluation entry, estimators) */
+  else if (k == "pair_kernel_warps_per_walker") *value = c->lean ? c->lean_cfg.nwarps_per_group : 0;
   else if (k == "kernel_variant") *value = c->ksel;
   else if (k == "pipeline") *value = c->pipeline;
+  else if (k == "pair_kernel") *value = c->lean ? 1 : 0;
+  else if (k == "pair_kernel_occupancy_target") *value = c->lean_occ;
   else if (k == "migration_events") *value = (double)c->mig_events;
   else if (k == "migrated_out") *value = (double)c->mig_out;
   else if (k == "migrated_in") *value = (double)c->mig_in;
@@ -2382,7 +2433,7 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "ctas_per_sm") *value = propagate_occupancy(c->ksel, c->has_hist, c->cfg.smem);
   else if (k == "launches") *value = (double)c->launches;
   else if (k == "sms") *value = c->sms;
-  else if (k == "regs_propagate") *value = propagate_regs(c->ksel, false);
+  else if (k == "regs_propagate") *value = c->lean ? pair_move_regs(c->lean_vk, c->lean_occ) : propagate_regs(c->ksel, false);
   else if (k == "regs_eval") *value = eval_regs(c->ksel, false);
   else if (k == "n_pair_passes") *value = c->plan.n2b;
   else if (k == "time_kernels_on") { c->time_kernels = 1; *value = 1; }

@@ -119,6 +119,17 @@ cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan 
                               const Ctl *ctl, double *hist, int occ, int grid);
 int estimator_occupancy(int occ, size_t smem);
 
+// the hot kernel of the one-species / one-pair-pass shapes (kernels_pair.cu): move step with the tournament tile schedule
+int pair_warps_per_walker(int n);
+size_t pair_group_bytes(const Plan &plan, int nwarps);
+size_t pair_cta_extra_bytes();
+void pair_exp_table(double *tab256);
+cudaError_t configure_kernels_pair(int max_smem_optin);
+int pair_move_occupancy(int vk, int occ, size_t smem);
+int pair_move_regs(int vk, int occ);
+cudaError_t launch_pair_move(int vk, int occ, const LaunchCfg &cfg, int grid, cudaStream_t st, const Plan &plan, const DmcParams &dmc,
+                             const double *dev_tab, const StepArgs &a, double *e_old);
+
 // forward walking (kernels_fw.cu)
 size_t fw_record_group_bytes(const Plan &plan, int max_sf_bins);
 cudaError_t configure_kernels_fw(int max_smem_optin);

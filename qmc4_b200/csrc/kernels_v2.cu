@@ -53,7 +53,11 @@ move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams
           for (int m = 0; m < 4; ++m)
             {
               const int k = c * 4 + m;
-              if (k < dofs) S.R[k] = fma(dmc.sqrt_tau, z[m], fma(dmc.tau, Fold[k], Rold[k]));
+              if (k < dofs)
+                {
+                  S.R[k] = fma(dmc.sqrt_tau, z[m], fma(dmc.tau, Fold[k], Rold[k]));
+                  if (a.trace.xi) a.trace.xi[(size_t)j * dofs + k] = z[m];
+                }
             }
         }
       G.sync();
@@ -110,6 +114,26 @@ move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams
           e_old[j] = Eold;            /* branching needs (E' + E)/2 (branching.cpp:13); decided in scan_v2 */
           a.flags[j] = accepted ? 1 : 0;
         }
+      if (a.trace.Rprop)
+        {
+          for (int k = G.gtid; k < dofs; k += G.gsize)
+            {
+              a.trace.Rprop[(size_t)j * dofs + k] = S.R[k];
+              a.trace.Fprop[(size_t)j * dofs + k] = S.acc[k];
+            }
+          if (G.gtid == 0)
+            {
+              a.trace.logpsi[j] = r.logpsi;
+              a.trace.lap[j] = r.lap;
+              a.trace.V[j] = r.V;
+              a.trace.Eprop[j] = Enew;
+              a.trace.q[j] = qs;
+              a.trace.u_m[j] = u_m;
+              a.trace.accepted[j] = accepted;
+              a.trace.valid[j] = r.valid;
+              a.trace.parent[j] = src;
+            }
+        }
       G.sync();
     }
 }
@@ -149,14 +173,16 @@ scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const do
               e[u] = a.out.E[j];
               nacc += a.flags[j] & 1;
               int nn = 1;
-              if (dmc.branching_on)
+              if (dmc.branching_on || a.trace.u_b)
                 {
                   const u32x4 rd = philox4x32_10({(uint32_t)j, 0xffffffffu, step_lo, step_hi}, dmc.seed_lo, dmc.seed_hi);
                   const double u_b = u01_53(rd.z, rd.w);
-                  nn = (int)(exp(-dmc.tau * (0.5 * (e[u] + e_old[j]) - eT)) + u_b);      /* branching.cpp:13 */
+                  if (dmc.branching_on) nn = (int)(exp(-dmc.tau * (0.5 * (e[u] + e_old[j]) - eT)) + u_b);      /* branching.cpp:13 */
+                  if (a.trace.u_b) a.trace.u_b[j] = u_b;
                 }
               n[u] = max(0, min(nn, a.cap));
               a.n_desc[j] = n[u];
+              if (a.trace.n_desc) a.trace.n_desc[j] = n[u];
             }
         }
       const int mine = n[0] + n[1] + n[2] + n[3];

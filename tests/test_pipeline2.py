@@ -18,6 +18,7 @@ def _run(pipeline, cfg, R, steps):
         os.environ["QMC4_PIPELINE"] = "1"
     else:
         os.environ.pop("QMC4_PIPELINE", None)       # pipeline 2 is the default
+    os.environ["QMC4_LEAN"] = "0"                   # the general kernels of both pipelines share every summation order
     try:
         s = System.from_input(cfg)
         assert s.info("pipeline") == pipeline
@@ -29,6 +30,7 @@ def _run(pipeline, cfg, R, steps):
         s.close()
     finally:
         os.environ.pop("QMC4_PIPELINE", None)
+        os.environ.pop("QMC4_LEAN", None)
     return b, Rn, En, g
 
 
@@ -52,3 +54,71 @@ def test_pipeline2_is_bitwise_pipeline1(name):
     if g1 is not None:
         assert g1[1] == g2[1]
         np.testing.assert_allclose(g1[0], g2[0], rtol=1e-12)
+
+
+def _traced(cfg, R, lean):
+    from qmc4_b200.system import System
+    os.environ["QMC4_LEAN"] = "1" if lean else "0"
+    try:
+        s = System.from_input(cfg)
+        assert s.info("pair_kernel") == (1 if lean else 0)
+        s.upload(R)
+        tr = s.step_traced(accumulate=bool(cfg["measurements"]))
+        Rn, En = s.download(with_energy=True)
+        b = s.block_results()
+        s.close()
+    finally:
+        os.environ.pop("QMC4_LEAN", None)
+    return tr, Rn, En, b
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+@pytest.mark.parametrize("N,L,pot", [(2, 3.0, "potentialBarrier"), (10, 3.0, "squareWell"), (16, 2.6, "potentialBarrier"), (17, 2.6, None), (31, 3.2, "potentialBarrier"), (32, 3.2, "potentialBarrier"), (33, 3.2, None), (64, 4.0, "potentialBarrier"),
+                                     (65, 4.0, "squareWell"), (100, 4.7, "potentialBarrier"), (160, 5.5, None), (256, 6.3496, "potentialBarrier"),
+                                     (512, 8.0, "potentialBarrier")])
+def test_pair_kernel_agrees_with_the_general_kernels(N, L, pot):
+    """the tournament-schedule kernel of the one-species / one-pair-pass shapes (kernels_pair.cu) against the general move
+    kernel on the same step: identical random numbers and proposals, identical decisions, sums that only differ by the order
+    of the floating-point additions"""
+    W = 24 if N <= 256 else 10
+    cfg = cases.pbc(N, L, pot=pot, walkers=W)
+    R = np.random.default_rng(N).uniform(-L, L, size=(W, 3 * N))
+    tg, Rg, Eg, bg = _traced(cfg, R, lean=False)
+    tl, Rl, El, bl = _traced(cfg, R, lean=True)
+    np.testing.assert_array_equal(tl["xi"], tg["xi"])
+    np.testing.assert_array_equal(tl["Rprop"], tg["Rprop"])
+    np.testing.assert_array_equal(tl["u_metropolis"], tg["u_metropolis"])
+    np.testing.assert_array_equal(tl["u_branch"], tg["u_branch"])
+    np.testing.assert_array_equal(tl["V"], tg["V"])                      # a pair count times V0: exact
+    assert _rel(tl["logpsi"], tg["logpsi"]) < 1e-13 and _rel(tl["lap"], tg["lap"]) < 1e-12
+    assert _rel(tl["Fprop"], tg["Fprop"]) < 1e-12 and _rel(tl["Eprop"], tg["Eprop"]) < 1e-11 and _rel(tl["q"], tg["q"]) < 1e-9
+    np.testing.assert_array_equal(tl["accepted"], tg["accepted"])
+    np.testing.assert_array_equal(tl["n_desc"], tg["n_desc"])
+    assert tl["n_after"] == tg["n_after"] and _rel(np.sort(El), np.sort(Eg)) < 1e-11
+    assert bl["n_moves"] == bg["n_moves"] == W and bl["n_accepted"] == bg["n_accepted"]
+
+
+@pytest.mark.parametrize("N,L", [(64, 4.0), (256, 6.3496), (512, 8.0)])
+def test_pair_kernel_traced_step_vs_oracle_at_baseline_sizes(port, N, L):
+    """BASELINE configs 2, 3, 5: proposal, evaluation, Green ratio and Metropolis decision of the production kernel against
+    dmcDriver::update restated in the oracle, given the random numbers the kernel drew"""
+    from qmc4_b200.system import System
+    W = 6
+    cfg = cases.pbc(N, L, walkers=W)
+    R = np.random.default_rng(1000 + N).uniform(-L / 2, L / 2, size=(W, 3 * N))
+    s = System.from_input(cfg)
+    assert s.info("pair_kernel") == 1
+    s.upload(R)
+    e0 = port.eval(cfg, R)
+    tr = s.step_traced()
+    ep = port.eval(cfg, tr["Rprop"])
+    for k, t in (("logpsi", "logpsi"), ("grad", "Fprop"), ("lap", "lap"), ("V", "V"), ("E", "Eprop")):
+        assert _rel(tr[t], ep[k]) < 1e-10, k
+    q = port.green_ratio(cfg, cfg["timeStep"], tr["Rprop"], ep["grad"], R, e0["grad"])
+    assert _rel(tr["q"], q) < 1e-9
+    up = port.update(cfg, cfg["timeStep"], R, tr["xi"], tr["u_metropolis"])
+    np.testing.assert_array_equal(up["accepted"], tr["accepted"])
+    s.close()
