@@ -150,7 +150,7 @@ struct qmc_ctx {
   unsigned long long *d_checksum = nullptr;
   // the hot kernel of the one-species / one-pair-pass shapes (kernels_pair.cu) replaces the general move kernel when the plan allows
   bool lean = false;
-  int lean_vk = V_NONE, lean_occ = 2;
+  int lean_vk = V_NONE, lean_occ = 0;      /* lean_occ: launch-geometry variant of kernels_pair.cu */
   LaunchCfg lean_cfg = {};
   double *lean_tab = nullptr;       // 2^(j/256), j = 0..255 (device)
   // QMC4_TRACE=n: device/host timeline of the first n steps of every qmc_step call, printed to stderr (diagnostics)
@@ -1480,21 +1480,17 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
     if (c->lean)
       {
         c->lean_vk = P.p2[0].vkind;
-        if (const char *o = getenv("QMC4_LEAN_OCC")) c->lean_occ = atoi(o) >= 3 ? 3 : 2;
+        if (const char *o = getenv("QMC4_LEAN_VARIANT")) c->lean_occ = std::max(0, std::min(2, atoi(o)));
         LaunchCfg &L = c->lean_cfg;
-        L.block = 256;
-        L.nwarps_per_group = pair_warps_per_walker(P.N[0]);
-        if (const char *w = getenv("QMC4_LEAN_WPW"))
-          {
-            const int v = atoi(w);
-            if (v == 1 || v == 2 || v == 4 || v == 8) L.nwarps_per_group = v;
-          }
-        L.groups_per_cta = 8 / L.nwarps_per_group;
+        L.block = pair_variant_threads(c->lean_occ);
+        L.nwarps_per_group = std::min(pair_warps_per_walker(P.N[0]), L.block / 32);
+        L.groups_per_cta = (L.block / 32) / L.nwarps_per_group;
         L.smem = pair_group_bytes(P, L.nwarps_per_group) * L.groups_per_cta + pair_cta_extra_bytes();
         if ((int)L.smem > c->max_smem) c->lean = false;
         else
           {
             int per_sm = std::max(1, std::min(pair_move_occupancy(c->lean_vk, c->lean_occ, L.smem), 2048 / L.block));
+            per_sm = std::min(per_sm, c->lean_occ == 2 ? 5 : c->lean_occ == 1 ? 4 : 2);
             if (const char *e2 = getenv("QMC4_CTAS_PER_SM"))
               {
                 const int v = atoi(e2);

@@ -123,6 +123,7 @@ int estimator_occupancy(int occ, size_t smem);
 int pair_warps_per_walker(int n);
 size_t pair_group_bytes(const Plan &plan, int nwarps);
 size_t pair_cta_extra_bytes();
+int pair_variant_threads(int variant);
 void pair_exp_table(double *tab256);
 cudaError_t configure_kernels_pair(int max_smem_optin);
 int pair_move_occupancy(int vk, int occ, size_t smem);

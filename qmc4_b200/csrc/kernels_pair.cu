@@ -13,12 +13,21 @@
 //    coordinate is stored twice, so lane l reads column (l+k) mod 32 at the fixed offset l+k: one running pointer and
 //    immediate offsets instead of a masked index computation per load.
 //  * the visitor accumulators rotate at the end of every step of a tile (no conditional in front of the shuffles).
+//  * minimum image in fixed point.  geometryPBC::difference (geometry.h:50) is t - round(t/L) L; here every coordinate of
+//    the configuration is converted once per move to a 64-bit fraction of the box, X = rint(frac(x/L) 2^64), and the
+//    minimum-image difference of a pair is the WRAPPING integer subtraction Xi - Xj: the two's-complement wrap-around is
+//    the periodic wrap.  Resolution L 2^-64 (5e-20 L) — finer than the rounding of x itself; the pair then costs one
+//    integer subtraction + one int64->fp64 conversion per component instead of 3 FP64-pipe instructions + FRND + LOP3.
+//    In a cubic box the pair sums stay in box units (all scale factors are folded into the constants on the host).
+//    Exact ties (t = +-L/2 to the last bit) map to -L/2 where the reference's round-half-away gives -sign(t) L/2: same
+//    distance, measure zero after one diffusion step (the evaluation entry qmc_eval keeps the reference's rounding).
 //
 // Reference semantics: dmcDriver::update (dmcDriver.cpp:56-84) = driftDiffusionFirstOrder::move (dmcMoves.cpp:12-30) +
 // tableDistances::update (tableDistances.cpp:81-108) + jastrowTwoBodyWavefunctionUndistinguishable::accumulateDerivatives
 // (jastrowWavefunctionTwoBody.h:124-164) + potentialTwoBody (potentialTwoBody.h:23-33) + energy (energy.cpp:6-35) +
 // transitionProbabilityRatio (dmcMoves.cpp:32-57) + metropolis::acceptLog (metropolis.cpp:5-29).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "kernels.cuh"
 #include "evaluate.cuh"
@@ -40,7 +49,22 @@ struct LeanParams {
   double v_val;
   long long thr_bits;  // bit pattern of the largest r2 inside the step potential: r2 >= 0, so the integer order is the fp64 order
   const double *tab;   // [256] 2^(j/256), global memory
+  // fixed-point minimum image: X = rint(frac(x Linv) 2^64); d = (double)(Xi - Xj) in units s_d = L_d 2^-64
+  double s[3];         // L_d 2^-64
+  double gs[3];        // sc * s_d : gradient = gs_d * sum e d'_d
+  int cubic;           // 1: k, c, c1..c4, lap1, thr_bits are expressed in r2' = sum d'^2 (box units); 0: d is scaled to real units first
 };
+
+QMC_DEVICE long long to_box_fraction(const double x, const double Linv)
+{
+  double u = x * Linv;
+  u -= rint(u);                                   /* [-0.5, 0.5] */
+  return __double2ll_rn(u * 18446744073709551616.0);      /* saturates at +-2^63: one unit of 5e-20 L */
+}
+QMC_DEVICE double fx_diff(const long long a, const long long b)
+{
+  return __ll2double_rn((long long)((unsigned long long)a - (unsigned long long)b));   /* wrapping subtraction = minimum image */
+}
 
 QMC_DEVICE double exp_tab(const double r2, const LeanParams &E, const double *tab)
 {
@@ -65,18 +89,22 @@ struct LeanSums {
 };
 
 constexpr int STRIP = 192;     // doubles per warp: x[64] y[64] z[64], every column twice
+#ifndef QMC_PAIR_UNROLL
+#define QMC_PAIR_UNROLL 1
+#endif
+constexpr int PAIR_UNROLL = QMC_PAIR_UNROLL;
 
 // One tile: rows = block rb (lane l owns row particle rb*32+l), columns = block cb.  DIAG: rb == cb, cyclic offsets 1..16
 // (offset 16 half-populated).  MASKED: the row and/or column block is the ragged last block of the species.
 // Two independent pairs per lane and step: stream 0 meets column (l + OFF0 + k), stream 1 column (l + OFF1 + k).
-template <int VK, bool DIAG, bool MASKED>
-QMC_DEVICE void lean_tile(const LeanParams &LP, const double *tab, const Box &box, const double *xs, const int n, const int rb,
-                          const int cb, double *T, const int lane, double *acc, LeanSums &S)
+template <int VK, bool CUBIC, bool DIAG, bool MASKED>
+QMC_DEVICE void lean_tile(const LeanParams &LP, const double *tab, const long long *xs, const int n, const int rb,
+                          const int cb, long long *T, const int lane, double *acc, LeanSums &S)
 {
   constexpr int IT = DIAG ? 8 : 16, OFF0 = DIAG ? 1 : 0, OFF1 = DIAG ? 9 : 16;
   const int ci = cb * 32 + lane;
   const bool cok = !MASKED || ci < n;
-  const double cx = cok ? xs[ci] : 0.0, cy = cok ? xs[n + ci] : 0.0, cz = cok ? xs[2 * n + ci] : 0.0;
+  const long long cx = cok ? xs[ci] : 0, cy = cok ? xs[n + ci] : 0, cz = cok ? xs[2 * n + ci] : 0;
   __syncwarp();                      /* the strip may still be read by a slower lane of the previous tile */
   T[lane] = cx;
   T[32 + lane] = cx;
@@ -86,31 +114,36 @@ QMC_DEVICE void lean_tile(const LeanParams &LP, const double *tab, const Box &bo
   T[160 + lane] = cz;
   const int ri = rb * 32 + lane;
   const bool rok = !MASKED || ri < n;
-  double xi = cx, yi = cy, zi = cz;
+  long long xi = cx, yi = cy, zi = cz;
   if (!DIAG)
     {
-      xi = rok ? xs[ri] : 0.0;
-      yi = rok ? xs[n + ri] : 0.0;
-      zi = rok ? xs[2 * n + ri] : 0.0;
+      xi = rok ? xs[ri] : 0;
+      yi = rok ? xs[n + ri] : 0;
+      zi = rok ? xs[2 * n + ri] : 0;
     }
   __syncwarp();
   double ax = 0, ay = 0, az = 0;
   double v0x = 0, v0y = 0, v0z = 0, v1x = 0, v1y = 0, v1z = 0;
   const int src = (lane + 1) & 31;
-  const double *P = T + lane;
+  const long long *P = T + lane;
   int ncol = MASKED ? n - cb * 32 : 32;       /* valid columns of the block (>= 32: all) */
 #pragma unroll 1
   for (int k = 0; k < IT; ++k)
     {
-      const double x0 = P[OFF0], y0 = P[64 + OFF0], z0 = P[128 + OFF0];
-      const double x1 = P[OFF1], y1 = P[64 + OFF1], z1 = P[128 + OFF1];
+      const long long x0 = P[OFF0], y0 = P[64 + OFF0], z0 = P[128 + OFF0];
+      const long long x1 = P[OFF1], y1 = P[64 + OFF1], z1 = P[128 + OFF1];
       ++P;
-      const double dx0 = min_image(xi - x0, box.Lx, box.ix);
-      const double dy0 = min_image(yi - y0, box.Ly, box.iy);
-      const double dz0 = min_image(zi - z0, box.Lz, box.iz);
-      const double dx1 = min_image(xi - x1, box.Lx, box.ix);
-      const double dy1 = min_image(yi - y1, box.Ly, box.iy);
-      const double dz1 = min_image(zi - z1, box.Lz, box.iz);
+      double dx0 = fx_diff(xi, x0), dy0 = fx_diff(yi, y0), dz0 = fx_diff(zi, z0);
+      double dx1 = fx_diff(xi, x1), dy1 = fx_diff(yi, y1), dz1 = fx_diff(zi, z1);
+      if (!CUBIC)
+        {
+          dx0 *= LP.s[0];
+          dy0 *= LP.s[1];
+          dz0 *= LP.s[2];
+          dx1 *= LP.s[0];
+          dy1 *= LP.s[1];
+          dz1 *= LP.s[2];
+        }
       const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
       const double r21 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
       double e0 = exp_tab(r20, LP, tab);
@@ -154,12 +187,12 @@ QMC_DEVICE void lean_tile(const LeanParams &LP, const double *tab, const Box &bo
       v1z = shfl_d(v1z, src);
     }
   /* the tile owns its row block and its column block for the whole round: plain read-modify-write, no atomics */
-  const double sc = LP.sc;
+  const double gx = CUBIC ? LP.gs[0] : LP.sc, gy = CUBIC ? LP.gs[1] : LP.sc, gz = CUBIC ? LP.gs[2] : LP.sc;
   if (rok)
     {
-      acc[ri] = fma(sc, ax, acc[ri]);
-      acc[n + ri] = fma(sc, ay, acc[n + ri]);
-      acc[2 * n + ri] = fma(sc, az, acc[2 * n + ri]);
+      acc[ri] = fma(gx, ax, acc[ri]);
+      acc[n + ri] = fma(gy, ay, acc[n + ri]);
+      acc[2 * n + ri] = fma(gz, az, acc[2 * n + ri]);
     }
   __syncwarp();
   {
@@ -168,16 +201,16 @@ QMC_DEVICE void lean_tile(const LeanParams &LP, const double *tab, const Box &bo
     const int c0 = cb * 32 + q0, c1 = cb * 32 + q1;
     if (!MASKED || c0 < n)
       {
-        acc[c0] = fma(sc, v0x, acc[c0]);
-        acc[n + c0] = fma(sc, v0y, acc[n + c0]);
-        acc[2 * n + c0] = fma(sc, v0z, acc[2 * n + c0]);
+        acc[c0] = fma(gx, v0x, acc[c0]);
+        acc[n + c0] = fma(gy, v0y, acc[n + c0]);
+        acc[2 * n + c0] = fma(gz, v0z, acc[2 * n + c0]);
       }
     __syncwarp();
     if (!MASKED || c1 < n)
       {
-        acc[c1] = fma(sc, v1x, acc[c1]);
-        acc[n + c1] = fma(sc, v1y, acc[n + c1]);
-        acc[2 * n + c1] = fma(sc, v1z, acc[2 * n + c1]);
+        acc[c1] = fma(gx, v1x, acc[c1]);
+        acc[n + c1] = fma(gy, v1y, acc[n + c1]);
+        acc[2 * n + c1] = fma(gz, v1z, acc[2 * n + c1]);
       }
     __syncwarp();
   }
@@ -187,22 +220,22 @@ QMC_DEVICE void lean_tile(const LeanParams &LP, const double *tab, const Box &bo
 // and meets column (l + k) mod 32 with BOTH, so one column load and one visitor rotation serve two pairs (3 LDS + 6 SHFL per
 // two pairs; lean_tile: 6 + 12).  The row gradients stay in registers over both column blocks of the 64-block m'.
 // Full blocks only (the caller falls back to lean_tile on ragged edges).
-template <int VK>
-QMC_DEVICE void lean_pairblock(const LeanParams &LP, const double *tab, const Box &box, const double *xs, const int n, const int m, const int mp,
-                               double *T, const int lane, double *acc, LeanSums &S)
+template <int VK, bool CUBIC>
+QMC_DEVICE void lean_pairblock(const LeanParams &LP, const double *tab, const long long *xs, const int n, const int m, const int mp,
+                               long long *T, const int lane, double *acc, LeanSums &S)
 {
   const int r0 = m * 64 + lane, r1 = r0 + 32;
-  const double x0 = xs[r0], y0 = xs[n + r0], z0 = xs[2 * n + r0];
-  const double x1 = xs[r1], y1 = xs[n + r1], z1 = xs[2 * n + r1];
+  const long long x0 = xs[r0], y0 = xs[n + r0], z0 = xs[2 * n + r0];
+  const long long x1 = xs[r1], y1 = xs[n + r1], z1 = xs[2 * n + r1];
   double a0x = 0, a0y = 0, a0z = 0, a1x = 0, a1y = 0, a1z = 0;
   const int src = (lane + 1) & 31;
-  const double sc = LP.sc;
+  const double gx = CUBIC ? LP.gs[0] : LP.sc, gy = CUBIC ? LP.gs[1] : LP.sc, gz = CUBIC ? LP.gs[2] : LP.sc;
 #pragma unroll 1
   for (int h = 0; h < 2; ++h)
     {
       const int cb = mp * 2 + h;
       const int ci = cb * 32 + lane;
-      const double cx = xs[ci], cy = xs[n + ci], cz = xs[2 * n + ci];
+      const long long cx = xs[ci], cy = xs[n + ci], cz = xs[2 * n + ci];
       __syncwarp();
       T[lane] = cx;
       T[32 + lane] = cx;
@@ -212,18 +245,23 @@ QMC_DEVICE void lean_pairblock(const LeanParams &LP, const double *tab, const Bo
       T[160 + lane] = cz;
       __syncwarp();
       double vx = 0, vy = 0, vz = 0;
-      const double *P = T + lane;
-#pragma unroll 1
+      const long long *P = T + lane;
+#pragma unroll PAIR_UNROLL
       for (int k = 0; k < 32; ++k)
         {
-          const double xc = P[0], yc = P[64], zc = P[128];
+          const long long xc = P[0], yc = P[64], zc = P[128];
           ++P;
-          const double dx0 = min_image(x0 - xc, box.Lx, box.ix);
-          const double dy0 = min_image(y0 - yc, box.Ly, box.iy);
-          const double dz0 = min_image(z0 - zc, box.Lz, box.iz);
-          const double dx1 = min_image(x1 - xc, box.Lx, box.ix);
-          const double dy1 = min_image(y1 - yc, box.Ly, box.iy);
-          const double dz1 = min_image(z1 - zc, box.Lz, box.iz);
+          double dx0 = fx_diff(x0, xc), dy0 = fx_diff(y0, yc), dz0 = fx_diff(z0, zc);
+          double dx1 = fx_diff(x1, xc), dy1 = fx_diff(y1, yc), dz1 = fx_diff(z1, zc);
+          if (!CUBIC)
+            {
+              dx0 *= LP.s[0];
+              dy0 *= LP.s[1];
+              dz0 *= LP.s[2];
+              dx1 *= LP.s[0];
+              dy1 *= LP.s[1];
+              dz1 *= LP.s[2];
+            }
           const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
           const double r21 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
           const double e0 = exp_tab(r20, LP, tab);
@@ -254,24 +292,25 @@ QMC_DEVICE void lean_pairblock(const LeanParams &LP, const double *tab, const Bo
           vz = shfl_d(vz, src);
         }
       /* after 32 rotations the visitor is back at the lane whose index is its column */
-      acc[ci] = fma(sc, vx, acc[ci]);
-      acc[n + ci] = fma(sc, vy, acc[n + ci]);
-      acc[2 * n + ci] = fma(sc, vz, acc[2 * n + ci]);
+      acc[ci] = fma(gx, vx, acc[ci]);
+      acc[n + ci] = fma(gy, vy, acc[n + ci]);
+      acc[2 * n + ci] = fma(gz, vz, acc[2 * n + ci]);
     }
-  acc[r0] = fma(sc, a0x, acc[r0]);
-  acc[n + r0] = fma(sc, a0y, acc[n + r0]);
-  acc[2 * n + r0] = fma(sc, a0z, acc[2 * n + r0]);
-  acc[r1] = fma(sc, a1x, acc[r1]);
-  acc[n + r1] = fma(sc, a1y, acc[n + r1]);
-  acc[2 * n + r1] = fma(sc, a1z, acc[2 * n + r1]);
+  acc[r0] = fma(gx, a0x, acc[r0]);
+  acc[n + r0] = fma(gy, a0y, acc[n + r0]);
+  acc[2 * n + r0] = fma(gz, a0z, acc[2 * n + r0]);
+  acc[r1] = fma(gx, a1x, acc[r1]);
+  acc[n + r1] = fma(gy, a1y, acc[n + r1]);
+  acc[2 * n + r1] = fma(gz, a1z, acc[2 * n + r1]);
   __syncwarp();
 }
 
 struct LeanScratch {
   double *R;        // [dofs] configuration being evaluated
   double *acc;      // [dofs] gradient accumulator (single copy)
+  long long *X;     // [dofs] the configuration as 64-bit fractions of the box
   double *red;      // [nwarps*4 + 8]
-  double *strip;    // this warp's column strip
+  long long *strip; // this warp's column strip
 };
 
 QMC_DEVICE LeanScratch make_lean_scratch(const Plan &plan, unsigned char *smem, int group_index, int nwarps, int gwarp, size_t group_bytes)
@@ -280,8 +319,9 @@ QMC_DEVICE LeanScratch make_lean_scratch(const Plan &plan, unsigned char *smem, 
   double *base = reinterpret_cast<double *>(smem + (size_t)group_index * group_bytes);
   S.R = base;
   S.acc = base + plan.dofs;
-  S.red = S.acc + plan.dofs;
-  S.strip = S.red + (nwarps * 4 + 8) + (size_t)gwarp * STRIP;
+  S.X = reinterpret_cast<long long *>(S.acc + plan.dofs);
+  S.red = S.acc + 2 * (size_t)plan.dofs;
+  S.strip = reinterpret_cast<long long *>(S.red + (nwarps * 4 + 8)) + (size_t)gwarp * STRIP;
   return S;
 }
 
@@ -289,12 +329,16 @@ QMC_DEVICE LeanScratch make_lean_scratch(const Plan &plan, unsigned char *smem, 
 // Schedule: the particles are cut in 64-blocks; the pairs of DIFFERENT 64-blocks are visited in the rounds of a round-robin
 // tournament (in one round every 64-block belongs to at most one warp, which therefore owns its gradient rows), then every
 // 64-block is paired with itself (two diagonal 32-tiles + one 32 x 32 tile).
-template <int VK>
+template <int VK, bool CUBIC>
 QMC_DEVICE EvalResult lean_evaluate(const Plan &plan, const LeanParams &LP, const double *tab, const LeanScratch &S, const Group &G)
 {
   const int n = plan.N[0], dofs = plan.dofs;
-  const Box box = {plan.L[0], plan.L[1], plan.L[2], plan.Linv[0], plan.Linv[1], plan.Linv[2]};
-  for (int k = G.gtid; k < dofs; k += G.gsize) S.acc[k] = 0.0;
+  for (int k = G.gtid; k < dofs; k += G.gsize)
+    {
+      S.acc[k] = 0.0;
+      const int d = k / n;                          /* walker layout: x[n] y[n] z[n] */
+      S.X[k] = to_box_fraction(S.R[k], plan.Linv[d]);
+    }
   G.sync();
   LeanSums sums = {0.0, 0.0, 0};
   const int nb = (n + 31) >> 5;                   /* 32-blocks */
@@ -320,14 +364,14 @@ QMC_DEVICE EvalResult lean_evaluate(const Plan &plan, const LeanParams &LP, cons
             }
           if (a >= nB || b >= nB) continue;        /* bye */
           const int M = a > b ? a : b, Mp = a > b ? b : a;
-          if (M * 64 + 64 <= n) lean_pairblock<VK>(LP, tab, box, S.R, n, M, Mp, S.strip, G.lane, S.acc, sums);
+          if (M * 64 + 64 <= n) lean_pairblock<VK, CUBIC>(LP, tab, S.X, n, M, Mp, S.strip, G.lane, S.acc, sums);
           else
             { /* ragged last 64-block: its one or two 32-blocks against the two (full) 32-blocks of Mp */
               for (int rb = 2 * M; rb < nb; ++rb)
                 for (int cb = 2 * Mp; cb < 2 * Mp + 2; ++cb)
                   {
-                    if (rb * 32 + 32 <= n) lean_tile<VK, false, false>(LP, tab, box, S.R, n, rb, cb, S.strip, G.lane, S.acc, sums);
-                    else lean_tile<VK, false, true>(LP, tab, box, S.R, n, rb, cb, S.strip, G.lane, S.acc, sums);
+                    if (rb * 32 + 32 <= n) lean_tile<VK, CUBIC, false, false>(LP, tab, S.X, n, rb, cb, S.strip, G.lane, S.acc, sums);
+                    else lean_tile<VK, CUBIC, false, true>(LP, tab, S.X, n, rb, cb, S.strip, G.lane, S.acc, sums);
                   }
             }
         }
@@ -336,19 +380,19 @@ QMC_DEVICE EvalResult lean_evaluate(const Plan &plan, const LeanParams &LP, cons
   for (int d = G.gwarp; d < nB; d += G.nwarps)
     {
       const int b0 = 2 * d, b1 = 2 * d + 1;
-      if (b0 * 32 + 32 <= n) lean_tile<VK, true, false>(LP, tab, box, S.R, n, b0, b0, S.strip, G.lane, S.acc, sums);
-      else lean_tile<VK, true, true>(LP, tab, box, S.R, n, b0, b0, S.strip, G.lane, S.acc, sums);
+      if (b0 * 32 + 32 <= n) lean_tile<VK, CUBIC, true, false>(LP, tab, S.X, n, b0, b0, S.strip, G.lane, S.acc, sums);
+      else lean_tile<VK, CUBIC, true, true>(LP, tab, S.X, n, b0, b0, S.strip, G.lane, S.acc, sums);
       if (b1 < nb)
         {
           if (b1 * 32 + 32 <= n)
             {
-              lean_tile<VK, true, false>(LP, tab, box, S.R, n, b1, b1, S.strip, G.lane, S.acc, sums);
-              lean_tile<VK, false, false>(LP, tab, box, S.R, n, b1, b0, S.strip, G.lane, S.acc, sums);
+              lean_tile<VK, CUBIC, true, false>(LP, tab, S.X, n, b1, b1, S.strip, G.lane, S.acc, sums);
+              lean_tile<VK, CUBIC, false, false>(LP, tab, S.X, n, b1, b0, S.strip, G.lane, S.acc, sums);
             }
           else
             {
-              lean_tile<VK, true, true>(LP, tab, box, S.R, n, b1, b1, S.strip, G.lane, S.acc, sums);
-              lean_tile<VK, false, true>(LP, tab, box, S.R, n, b1, b0, S.strip, G.lane, S.acc, sums);
+              lean_tile<VK, CUBIC, true, true>(LP, tab, S.X, n, b1, b1, S.strip, G.lane, S.acc, sums);
+              lean_tile<VK, CUBIC, false, true>(LP, tab, S.X, n, b1, b0, S.strip, G.lane, S.acc, sums);
             }
         }
     }
@@ -381,18 +425,18 @@ QMC_DEVICE EvalResult lean_evaluate(const Plan &plan, const LeanParams &LP, cons
   return out;
 }
 
-template <int VK, int MINB>
-__global__ void __launch_bounds__(CTA_THREADS, MINB)
+template <int VK, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 pair_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams dmc, const __grid_constant__ LeanParams LP, const StepArgs a,
                  double *e_old, int nwarps_per_group, size_t group_bytes)
 {
   QMC_DYNAMIC_SMEM(smem);
   const Group G = make_group(nwarps_per_group);
-  const int groups = (CTA_THREADS / 32) / nwarps_per_group;
+  const int groups = (THREADS / 32) / nwarps_per_group;
   const int g = (threadIdx.x >> 5) / nwarps_per_group;
-  const LeanScratch S = make_lean_scratch(plan, smem, g, nwarps_per_group, G.gwarp, group_bytes);
-  double *tab = reinterpret_cast<double *>(smem + (size_t)groups * group_bytes);        /* 2^(j/256), shared by the CTA */
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = LP.tab[i];
+  double *tab = reinterpret_cast<double *>(smem);        /* 2^(j/256) at the start of the CTA's shared memory (fixed address) */
+  const LeanScratch S = make_lean_scratch(plan, smem + 256 * sizeof(double), g, nwarps_per_group, G.gwarp, group_bytes);
+  for (int i = threadIdx.x; i < 256; i += THREADS) tab[i] = LP.tab[i];
   __syncthreads();
   const int dofs = plan.dofs;
   const Ctl *ctl = a.ctl;
@@ -425,7 +469,7 @@ pair_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
             }
         }
       G.sync();
-      const EvalResult r = lean_evaluate<VK>(plan, LP, tab, S, G);
+      const EvalResult r = LP.cubic ? lean_evaluate<VK, true>(plan, LP, tab, S, G) : lean_evaluate<VK, false>(plan, LP, tab, S, G);
       // ---- log Green ratio and |grad|^2
       double q = 0, f2 = 0;
       for (int k = G.gtid; k < dofs; k += G.gsize)
@@ -505,20 +549,22 @@ pair_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
 }
 
 #ifdef QMC_EMULATE   /* tests/emu: cudaLaunchKernel gets a trampoline that unpacks the argument array */
-template <int VK, int MINB> void pair_tramp(void **p)
+template <int VK, int THREADS, int MINB> void pair_tramp(void **p)
 {
-  pair_move_kernel<VK, MINB>(*(Plan *)p[0], *(DmcParams *)p[1], *(LeanParams *)p[2], *(StepArgs *)p[3], *(double **)p[4], *(int *)p[5], *(size_t *)p[6]);
+  pair_move_kernel<VK, THREADS, MINB>(*(Plan *)p[0], *(DmcParams *)p[1], *(LeanParams *)p[2], *(StepArgs *)p[3], *(double **)p[4], *(int *)p[5],
+                                      *(size_t *)p[6]);
 }
-template <int VK, int MINB> const void *pair_fn() { return (const void *)&pair_tramp<VK, MINB>; }
+template <int VK, int THREADS, int MINB> const void *pair_fn() { return (const void *)&pair_tramp<VK, THREADS, MINB>; }
 #else
-template <int VK, int MINB> const void *pair_fn() { return (const void *)pair_move_kernel<VK, MINB>; }
+template <int VK, int THREADS, int MINB> const void *pair_fn() { return (const void *)pair_move_kernel<VK, THREADS, MINB>; }
 #endif
 
-const void *pair_ptr(int vk, int occ)
+// launch geometries compiled: variant 0 = 256 threads x 2 CTAs/SM (<= 128 registers), 1 = 128 x 4, 2 = 128 x 5 (<= 96 registers)
+template <int VK> const void *pair_variant(int v)
 {
-  if (vk == V_STEP) return occ >= 3 ? pair_fn<V_STEP, 3>() : pair_fn<V_STEP, 2>();
-  return occ >= 3 ? pair_fn<V_NONE, 3>() : pair_fn<V_NONE, 2>();
+  return v == 2 ? pair_fn<VK, 128, 5>() : v == 1 ? pair_fn<VK, 128, 4>() : pair_fn<VK, 256, 2>();
 }
+const void *pair_ptr(int vk, int v) { return vk == V_STEP ? pair_variant<V_STEP>(v) : pair_variant<V_NONE>(v); }
 
 } // namespace
 
@@ -533,7 +579,7 @@ int pair_warps_per_walker(int n)
 
 size_t pair_group_bytes(const Plan &plan, int nwarps)
 {
-  size_t d = (size_t)2 * plan.dofs + (nwarps * 4 + 8) + (size_t)nwarps * STRIP;
+  size_t d = (size_t)3 * plan.dofs + (nwarps * 4 + 8) + (size_t)nwarps * STRIP;
   d = (d + 1) & ~(size_t)1;
   return d * 8;
 }
@@ -548,7 +594,7 @@ void pair_exp_table(double *tab256)
 cudaError_t configure_kernels_pair(int max_smem_optin)
 {
   for (int vk : {(int)V_STEP, (int)V_NONE})
-    for (int occ = 2; occ <= 3; ++occ)
+    for (int occ = 0; occ <= 2; ++occ)
       {
         cudaError_t e = cudaFuncSetAttribute(pair_ptr(vk, occ), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
         if (e != cudaSuccess) return e;
@@ -556,10 +602,12 @@ cudaError_t configure_kernels_pair(int max_smem_optin)
   return cudaSuccess;
 }
 
+int pair_variant_threads(int v) { return v == 0 ? 256 : 128; }
+
 int pair_move_occupancy(int vk, int occ, size_t smem)
 {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pair_ptr(vk, occ), CTA_THREADS, smem) != cudaSuccess) return 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pair_ptr(vk, occ), pair_variant_threads(occ), smem) != cudaSuccess) return 1;
   return n < 1 ? 1 : n;
 }
 
@@ -577,20 +625,32 @@ cudaError_t launch_pair_move(int vk, int occ, const LaunchCfg &cfg, int grid, cu
   size_t gb = (cfg.smem - pair_cta_extra_bytes()) / cfg.groups_per_cta;
   /* constants of the pair loop, folded on the host (jastrowGaussGauss.h:19-21: u = u0 exp(-alpha r^2), alpha = 1/(2 r0^2)) */
   const PairPass &PP = plan.p2[0];
-  const long double al = PP.J.p[0], u0 = PP.J.p[1], ln2 = 0.693147180559945309417232121458176568L;
+  const long double al = PP.J.p[0], ln2 = 0.693147180559945309417232121458176568L;
+  const long double two64 = 18446744073709551616.0L;
   LeanParams LP;
-  LP.k = (double)(-al * 256.0L / ln2);
-  LP.c = (double)(ln2 / (256.0L * al));
-  LP.c1 = (double)(-al);
-  LP.c2 = (double)(al * al / 2.0L);
-  LP.c3 = (double)(-al * al * al / 6.0L);
-  LP.c4 = (double)(al * al * al * al / 24.0L);
+  LP.cubic = (plan.L[0] == plan.L[1] && plan.L[1] == plan.L[2]) ? 1 : 0;
+  if (const char *e = getenv("QMC4_LEAN_NONCUBIC"))      /* test hook: run a cubic box through the per-dimension path */
+    if (atoi(e)) LP.cubic = 0;
+  for (int d = 0; d < 3; ++d) LP.s[d] = (double)((long double)plan.L[d] / two64);
+  /* cubic box: the pair sums are taken over d' = d / s (box units); every constant absorbs the factor s^2 */
+  const long double s2 = LP.cubic ? ((long double)plan.L[0] / two64) * ((long double)plan.L[0] / two64) : 1.0L;
+  const long double a2 = al * s2;                    /* exp(-alpha r2) = exp(-a2 r2') */
+  LP.k = (double)(-a2 * 256.0L / ln2);
+  LP.c = (double)(ln2 / (256.0L * a2));
+  LP.c1 = (double)(-a2);
+  LP.c2 = (double)(a2 * a2 / 2.0L);
+  LP.c3 = (double)(-a2 * a2 * a2 / 6.0L);
+  LP.c4 = (double)(a2 * a2 * a2 * a2 / 24.0L);
   LP.sc = -2.0 * PP.J.p[1] * PP.J.p[0];
+  for (int d = 0; d < 3; ++d) LP.gs[d] = (double)((long double)LP.sc * ((long double)plan.L[d] / two64));
   LP.u0 = PP.J.p[1];
   LP.lap0 = -12.0 * PP.J.p[0] * PP.J.p[1];
-  LP.lap1 = 8.0 * PP.J.p[0] * PP.J.p[0] * PP.J.p[1];
+  LP.lap1 = (double)(8.0L * al * al * (long double)PP.J.p[1] * s2);
   LP.v_val = PP.v_val;
-  memcpy(&LP.thr_bits, &PP.v_thr2, 8);
+  {
+    const double thr = (double)((long double)PP.v_thr2 / s2);       /* r2' <= thr  <=>  r2 <= v_thr2 (up to the last bit) */
+    memcpy(&LP.thr_bits, &thr, 8);
+  }
   LP.tab = dev_tab;
   void *args[] = {(void *)&plan, (void *)&dmc, (void *)&LP, (void *)&a, (void *)&e_old, (void *)&nw, (void *)&gb};
   return cudaLaunchKernel(pair_ptr(vk, occ), dim3(grid), dim3(cfg.block), args, cfg.smem, st);

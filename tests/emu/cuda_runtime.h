@@ -139,6 +139,13 @@ static inline long long __double_as_longlong(double d)
   std::memcpy(&u, &d, 8);
   return u;
 }
+static inline long long __double2ll_rn(double d)
+{ /* cvt.rni.s64.f64 saturates */
+  if (d >= 9223372036854775807.0) return 9223372036854775807LL;
+  if (d <= -9223372036854775808.0) return (-9223372036854775807LL - 1);
+  return std::llrint(d);
+}
+static inline double __ll2double_rn(long long v) { return (double)v; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline float emu_log2f(float x) { return log2f(x); }
 static inline void emu_sincosf(float x, float *s, float *c)

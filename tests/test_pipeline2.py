@@ -101,6 +101,26 @@ def test_pair_kernel_agrees_with_the_general_kernels(N, L, pot):
     assert bl["n_moves"] == bg["n_moves"] == W and bl["n_accepted"] == bg["n_accepted"]
 
 
+@pytest.mark.parametrize("N", [40, 130])
+def test_pair_kernel_in_a_non_cubic_box(port, N):
+    """per-dimension box scales of the fixed-point minimum image (kernels_pair.cu), against the general kernels and the oracle"""
+    W = 12
+    box = [3.0, 3.7, 4.4] if N == 40 else [4.6, 5.3, 6.1]
+    cfg = cases.pbc(N, box[0], walkers=W)
+    cfg["lBox"] = box
+    R = np.random.default_rng(7 * N).uniform(-1.0, 1.0, size=(W, 3, N)) * np.asarray(box)[None, :, None]
+    R = R.reshape(W, 3 * N)
+    tg, Rg, Eg, bg = _traced(cfg, R, lean=False)
+    tl, Rl, El, bl = _traced(cfg, R, lean=True)
+    np.testing.assert_array_equal(tl["Rprop"], tg["Rprop"])
+    np.testing.assert_array_equal(tl["V"], tg["V"])
+    assert _rel(tl["Fprop"], tg["Fprop"]) < 1e-12 and _rel(tl["Eprop"], tg["Eprop"]) < 1e-11 and _rel(tl["logpsi"], tg["logpsi"]) < 1e-13
+    np.testing.assert_array_equal(tl["accepted"], tg["accepted"])
+    ep = port.eval(cfg, tl["Rprop"])
+    for k, t in (("logpsi", "logpsi"), ("grad", "Fprop"), ("lap", "lap"), ("V", "V"), ("E", "Eprop")):
+        assert _rel(tl[t], ep[k]) < 1e-10, k
+
+
 @pytest.mark.parametrize("N,L", [(64, 4.0), (256, 6.3496), (512, 8.0)])
 def test_pair_kernel_traced_step_vs_oracle_at_baseline_sizes(port, N, L):
     """BASELINE configs 2, 3, 5: proposal, evaluation, Green ratio and Metropolis decision of the production kernel against
