@@ -149,6 +149,9 @@ struct qmc_ctx {
   bool p2p_connected = false;       // every directed pair of ranks has exchanged a message (NCCL connects lazily: ~140 ms per pair)
   unsigned long long *d_checksum = nullptr;
   // the hot kernel of the one-species / one-pair-pass shapes (kernels_pair.cu) replaces the general move kernel when the plan allows
+  bool trip_cyclic = false;
+  int trip_mod = 0;
+  int *trip_tab = nullptr;
   bool lean = false;
   int lean_vk = V_NONE, lean_occ = 0;      /* lean_occ: launch-geometry variant of kernels_pair.cu */
   LaunchCfg lean_cfg = {};
@@ -489,6 +492,7 @@ int build_plan(qmc_ctx *c)
             {
               T.has_constraint = 1;
               T.hs_R0 = w.hs;
+              T.hs_thr2 = step_threshold(w.hs);
             }
         }
       else if (w.kind == QMC_WF_JASTROW3B_DIS)
@@ -547,6 +551,7 @@ int build_plan(qmc_ctx *c)
             }
           T->has_pot = 1;
           T->v_R0 = v.p[0];
+          T->v_thr2 = step_threshold(v.p[0]);
           T->v_val = (v.kind == QMC_POT_THREEBODY_UNDIS_SQUAREWELL) ? -v.p[1] : v.p[1];   /* potentialFunctors.h:9,26 */
         }
       else if (v.kind == QMC_POT_THREEBODY_DIS_SQUAREWELL || v.kind == QMC_POT_THREEBODY_DIS_BARRIER)
@@ -669,6 +674,25 @@ int build_plan(qmc_ctx *c)
   const int nb = (maxN + 31) / 32, tiles = nb * (nb + 1) / 2;
   int wpw = tiles <= 3 ? 1 : tiles <= 10 ? 2 : tiles <= 36 ? 4 : 8;
   if (P.n3b > 0) wpw = 8;
+  /* cyclic triplet schedule (every triplet once): all undistinguishable triplet passes on sets of one size M, 3 <= M <= 32 */
+  int trip_mod = 0;
+  bool cyclic = P.n3b > 0;
+  for (int t = 0; t < P.n3b; ++t)
+    {
+      const TripletPass &T = P.p3[t];
+      if (T.setB >= 0) cyclic = false;
+      else if (trip_mod == 0) trip_mod = P.N[T.set];
+      else if (trip_mod != P.N[T.set]) cyclic = false;
+    }
+  if (trip_mod < 3 || trip_mod > 32) cyclic = false;
+  for (int e = 0; e < P.nest; ++e)
+    if (P.est[e].kind == QMC_EST_TRIMERCORRELATION || P.est[e].kind == QMC_EST_TRIMERCORRELATION_DIS || P.est[e].kind == QMC_EST_TRIMERHYPERRADIUS)
+      cyclic = false;
+  if (const char *e = getenv("QMC4_TRIPLET_CYCLIC"))
+    if (atoi(e) == 0) cyclic = false;
+  c->trip_cyclic = cyclic;
+  c->trip_mod = cyclic ? trip_mod : 0;
+  if (cyclic) wpw = 2;
   if (const char *e = getenv("QMC4_WPW"))
     {
       int v = atoi(e);
@@ -688,6 +712,7 @@ int build_plan(qmc_ctx *c)
         const int a = P.N[P.est[e].setA], b = P.N[P.est[e].setB], cc = P.N[P.est[e].setC];
         tab = std::max(tab, a * b + b * cc + a * cc);
       }
+  if (c->trip_cyclic) tab = std::max(tab, 1024 * (1 + wpw));      /* r2[32][32] + one weight table per warp */
   P.needs_pair_table = tab;
   P.aux_doubles = max_sf_bins * 2 * wpw;
   c->max_sf_bins = max_sf_bins;
@@ -1217,6 +1242,7 @@ void qmc_destroy(qmc_ctx *c)
   cudaFree(c->flags);
   cudaFree(c->d_checksum);
   cudaFree(c->lean_tab);
+  cudaFree(c->trip_tab);
   if (c->h_sums) cudaFreeHost(c->h_sums);
   if (c->ev_scan) cudaEventDestroy(c->ev_scan);
   if (c->ev_ar) cudaEventDestroy(c->ev_ar);
@@ -1513,12 +1539,36 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
       CK(cudaMalloc(&c->coef, c->coefpool.size() * 8));
       CK(cudaMemcpy(c->coef, c->coefpool.data(), c->coefpool.size() * 8, cudaMemcpyHostToDevice));
     }
+  if (c->trip_cyclic)
+    { /* canonical offset pairs (p, q) modulo M: gaps (p, q-p, M-q) equal to their lexicographically smallest rotation */
+      const int M = c->trip_mod;
+      std::vector<int> tabv;
+      for (int p = 1; p < M; ++p)
+        for (int q = p + 1; q < M; ++q)
+          {
+            const int g[3] = {p, q - p, M - q};
+            bool canon = true, sym = true;
+            for (int r = 1; r < 3; ++r)
+              {
+                const int h[3] = {g[r], g[(r + 1) % 3], g[(r + 2) % 3]};
+                if (std::lexicographical_compare(h, h + 3, g, g + 3)) canon = false;
+                if (h[0] != g[0] || h[1] != g[1] || h[2] != g[2]) sym = false;
+              }
+            if (canon) tabv.push_back(p | (q << 8) | ((sym ? 1 : 0) << 16));
+          }
+      CK(cudaMalloc(&c->trip_tab, tabv.size() * sizeof(int)));
+      CK(cudaMemcpy(c->trip_tab, tabv.data(), tabv.size() * sizeof(int), cudaMemcpyHostToDevice));
+      c->plan.trip_tab = c->trip_tab;
+      c->plan.trip_count = (int)tabv.size();
+      c->plan.trip_mod = M;
+    }
   if (c->plan.hist_stride > 0)
     {
       c->plan.hist_replicas = c->cfg.grid;
       c->est_grid = c->cfg.grid;
       if (c->pipeline == 2)
         { /* the estimator kernel of pipeline 2 has its own occupancy target (QMC4_EST_OCC = 2|3|4 resident CTAs per SM) */
+          if (c->max_sf_bins > 0) c->est_occ = 2;      /* the structure factor carries 8 phasors per thread in registers */
           if (const char *e = getenv("QMC4_EST_OCC"))
             {
               const int v = atoi(e);
@@ -2408,6 +2458,8 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "kernel_variant") *value = c->ksel;
   else if (k == "pipeline") *value = c->pipeline;
   else if (k == "pair_kernel") *value = c->lean ? 1 : 0;
+  else if (k == "triplet_cyclic") *value = c->trip_cyclic ? 1 : 0;
+  else if (k == "triplet_table_entries") *value = c->plan.trip_count;
   else if (k == "pair_kernel_occupancy_target") *value = c->lean_occ;
   else if (k == "migration_events") *value = (double)c->mig_events;
   else if (k == "migrated_out") *value = (double)c->mig_out;

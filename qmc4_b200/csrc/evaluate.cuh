@@ -625,6 +625,120 @@ QMC_DEVICE void run_triplet_pass(const Plan &plan, const TripletPass &T, const d
 }
 
 // ---------------------------------------------------------------------------------------------
+// Triplet pass, every unordered triplet ONCE (jastrowWavefunctionThreeBody.h:91-137 visits i<j<k once; so does this).
+// For a set of M <= 32 particles lane l owns particle l and meets the triplets (l, l+p, l+q) mod M for the canonical offset
+// pairs (p, q) of the host-built table: the three gaps (p, q-p, M-q) of a triplet are defined up to rotation, the table keeps
+// the lexicographically smallest rotation, so the M lanes x table entries enumerate each triplet exactly once (the fully
+// symmetric gap triple M/3,M/3,M/3 has only M/3 distinct triplets: lanes < M/3).  All M lanes work at every step.
+// The O(M^3) part only needs the pair table r2[gap][lane] (r2 between l and l+gap) and produces the symmetric pair weights
+// G[gap][lane] += u'(R)/R with three conflict-free shared-memory read-modify-writes (distinct lanes hit distinct slots);
+// an O(M^2) sweep turns the weights into gradients.  gaussiangaussian: u'/R = -2 alpha u, so R itself is never needed.
+QMC_DEVICE int wrap_mod(int i, int M) { return i >= M ? i - M : i; }
+
+QMC_DEVICE void run_triplet_pass_cyclic(const Plan &plan, const TripletPass &T, const double *coef, const Scratch &S, const Group &G,
+                                        double &lp, double &lap, double &V, int &invalid)
+{
+  const int s = T.set, M = plan.N[s];
+  const double *x = S.R + plan.off[s];
+  double *r2t = S.tab;                                   /* [32][32]: r2t[d*32 + l] = |r_l - r_(l+d)|^2, d = 1..M-1 */
+  double *Gw = S.tab + 1024 + (size_t)G.gwarp * 1024;    /* this warp's private pair weights, same indexing */
+  double *Gt = S.tab + 1024;                             /* after the reduction: warp 0's table holds the totals */
+  const Box box = {plan.L[0], plan.L[1], plan.L[2], plan.Linv[0], plan.Linv[1], plan.Linv[2]};
+  const int lane = G.lane;
+  for (int d = 1 + G.gwarp; d < M; d += G.nwarps)
+    if (lane < M)
+      {
+        const int b = wrap_mod(lane + d, M);
+        const double dx = min_image(x[lane] - x[b], box.Lx, box.ix);
+        const double dy = min_image(x[M + lane] - x[M + b], box.Ly, box.iy);
+        const double dz = min_image(x[2 * M + lane] - x[2 * M + b], box.Lz, box.iz);
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);      /* the reference squares the rounded norms */
+        r2t[d * 32 + lane] = r * r;
+      }
+  for (int k = lane; k < 1024; k += 32) Gw[k] = 0.0;
+  G.sync();
+  const bool gg = T.J.kind == J_GAUSSGAUSS;
+  double se = 0, ser = 0;
+  int npot = 0;
+  for (int t = G.gwarp; t < plan.trip_count; t += G.nwarps)
+    {
+      const int ent = plan.trip_tab[t];
+      const int p = ent & 255, q = (ent >> 8) & 255, sym = ent >> 16;
+      const bool act = lane < (sym ? M / 3 : M);
+      const int lb = wrap_mod(lane + p, M), lc = wrap_mod(lane + q, M);
+      const int ia = p * 32 + lane, ib = (q - p) * 32 + lb, ic = (M - q) * 32 + lc;
+      double w = 0.0;
+      if (act)
+        {
+          const double R2 = r2t[ia] + r2t[ic] + r2t[ib];
+          if (gg)
+            {
+              const double e = exp_gg(R2, T.J.p);
+              se += e;
+              ser = fma(e, R2, ser);
+              w = e;
+            }
+          else if (T.J.kind != J_NONE)
+            {
+              const double R = sqrt(R2);
+              double d0, d1, d2;
+              eval_radial(T.J, coef, R, d0, d1, d2);
+              w = d1 / R;
+              lp += d0;
+              lap += d2 * 3 + 3 * w * 5;          /* (2D-1) = 5 */
+            }
+          if (T.has_pot && R2 <= T.v_thr2) npot += 1;
+          if (T.has_constraint && R2 <= T.hs_thr2) invalid = 1;
+        }
+      if (T.J.kind != J_NONE)
+        {
+          if (act) Gw[ia] += w;
+          __syncwarp();
+          if (act) Gw[ib] += w;
+          __syncwarp();
+          if (act) Gw[ic] += w;
+          __syncwarp();
+        }
+    }
+  if (gg)
+    { /* u = u0 e ; u'/R = -2 a u ; 3u'' + 15 u'/R = u0 e (12 a^2 R^2 - 36 a) */
+      const double a = T.J.p[0], u0 = T.J.p[1];
+      lp += u0 * se;
+      lap += u0 * (12.0 * a * a * ser - 36.0 * a * se);
+    }
+  V += T.v_val * (double)npot;
+  G.sync();
+  if (T.J.kind != J_NONE)
+    {
+      for (int k = G.gtid; k < 1024; k += G.gsize)
+        {
+          double g = Gt[k];
+          for (int w = 1; w < G.nwarps; ++w) g += Gt[(size_t)w * 1024 + k];
+          Gt[k] = g;
+        }
+      G.sync();
+      const double scale = gg ? -2.0 * T.J.p[0] * T.J.p[1] : 1.0;
+      double *accw = S.acc + (size_t)G.gwarp * plan.dofs + plan.off[s];
+      for (int a = G.gtid; a < M; a += G.gsize)
+        {
+          double gx = 0, gy = 0, gz = 0;
+          for (int d = 1; d < M; ++d)
+            {
+              const int b = wrap_mod(a + d, M);
+              const double w = Gt[d * 32 + a] + Gt[(M - d) * 32 + b];      /* the pair (a, b) seen from a and from b */
+              gx = fma(w, min_image(x[a] - x[b], box.Lx, box.ix), gx);
+              gy = fma(w, min_image(x[M + a] - x[M + b], box.Ly, box.iy), gy);
+              gz = fma(w, min_image(x[2 * M + a] - x[2 * M + b], box.Lz, box.iz), gz);
+            }
+          accw[a] = fma(scale, gx, accw[a]);
+          accw[M + a] = fma(scale, gy, accw[M + a]);
+          accw[2 * M + a] = fma(scale, gz, accw[2 * M + a]);
+        }
+    }
+  G.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Distinguishable triplet pass on three different sets (A,B,C): jastrow3bDis
 // (jastrowWavefunctionThreeBody.h:170-300), potentialThreeBodyDis (potentialThreeBody.h:62-120),
 // hardSphereConstraintThreeBodyDis (jastrowWavefunctionThreeBody.cpp:54-80); triplets (i in A, j in B,
@@ -885,7 +999,9 @@ QMC_DEVICE EvalResult evaluate_walker(const Plan &plan, const double *coef, cons
       G.sync();
       for (int t = 0; t < plan.n3b; ++t)
         {
-          if (plan.p3[t].setB < 0) run_triplet_pass(plan, plan.p3[t], coef, S, G, H, lp, lap, V, invalid);
+          if (plan.p3[t].setB < 0 && plan.trip_tab && plan.N[plan.p3[t].set] == plan.trip_mod)
+            run_triplet_pass_cyclic(plan, plan.p3[t], coef, S, G, lp, lap, V, invalid);
+          else if (plan.p3[t].setB < 0) run_triplet_pass(plan, plan.p3[t], coef, S, G, H, lp, lap, V, invalid);
           else
             {
               const TripletSums ts = run_triplet_pass_dis(plan, t, coef, cold_args(S, G));
@@ -1235,6 +1351,42 @@ QMC_DEVICE void post_estimators(const Plan &plan, const Scratch &S, const Group 
       const double *x = S.R + plan.off[T.set];
       double *r2tab = S.tab;
       G.sync();
+      if (plan.trip_tab && n == plan.trip_mod)
+        { /* cyclic schedule (run_triplet_pass_cyclic): r2[gap][lane] table, every triplet once, sqrt / divide / atomic only for the
+             triplets inside the histogram range */
+          const int M = n, lane = G.lane;
+          for (int d = 1 + G.gwarp; d < M; d += G.nwarps)
+            if (lane < M)
+              {
+                const int b = wrap_mod(lane + d, M);
+                const double dx = min_image(x[lane] - x[b], box.Lx, box.ix);
+                const double dy = min_image(x[M + lane] - x[M + b], box.Ly, box.iy);
+                const double dz = min_image(x[2 * M + lane] - x[2 * M + b], box.Lz, box.iz);
+                const double r = sqrt(dx * dx + dy * dy + dz * dz);
+                r2tab[d * 32 + lane] = r * r;
+              }
+          G.sync();
+          const double pre = est.maxx * est.maxx * (1.0 + 1e-12);
+          for (int t = G.gwarp; t < plan.trip_count; t += G.nwarps)
+            {
+              const int ent = plan.trip_tab[t];
+              const int p = ent & 255, q = (ent >> 8) & 255, sym = ent >> 16;
+              if (lane >= (sym ? M / 3 : M)) continue;
+              const int lb = wrap_mod(lane + p, M), lc = wrap_mod(lane + q, M);
+              const double R2 = r2tab[p * 32 + lane] + r2tab[(M - q) * 32 + lc] + r2tab[(q - p) * 32 + lb];
+              if (R2 < pre)
+                {
+                  const double R = sqrt(R2);
+                  if (R < est.maxx)
+                    {
+                      const int bin = (int)((R - est.minx) * est.dxinv);
+                      if (bin >= 0) atomicAdd(hist + min(bin, est.bins - 1), hw / (R * R));
+                    }
+                }
+            }
+          G.sync();
+          continue;
+        }
       for (int k = G.gtid; k < P; k += G.gsize)
         {
           int a = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)k)) * 0.5f);
@@ -1281,12 +1433,71 @@ QMC_DEVICE void post_estimators(const Plan &plan, const Scratch &S, const Group 
       double *auxw = S.aux + (size_t)G.gwarp * 2 * bins;
       constexpr int CH = 8;
       G.sync();
+      const int nsets = (est.setA == est.setB) ? 1 : 2;
+      const int nA = plan.N[est.setA], ntot = nA + (nsets == 2 ? plan.N[est.setB] : 0);
+      constexpr int PMAX = 8;          /* particles per thread whose phasors are carried in registers */
+      if (ntot <= PMAX * G.gsize)
+        { /* e^{i q_j x} = e^{i q_0 x} (e^{i dq x})^j: two sincos per particle in all, the phasor of every particle advances through
+             the whole q grid by the complex recurrence (4 FP64 per point); rounding grows like bins x 1e-16 */
+          double pc[PMAX], ps[PMAX], pdc[PMAX], pds[PMAX];
+#pragma unroll
+          for (int p = 0; p < PMAX; ++p)
+            {
+              const int i = G.gtid + p * G.gsize;
+              pc[p] = ps[p] = pdc[p] = pds[p] = 0.0;
+              if (i < ntot)
+                {
+                  const bool inA = i < nA;
+                  const double x = inA ? S.R[plan.off[est.setA] + i] : S.R[plan.off[est.setB] + (i - nA)];      /* coordinate 0 */
+                  const double cf = inA ? 1.0 : (double)est.channel;
+                  double s0, c0;
+                  sincos(est.q0 * x, &s0, &c0);
+                  sincos(est.dq * x, &pds[p], &pdc[p]);
+                  pc[p] = c0 * cf;
+                  ps[p] = s0 * cf;
+                }
+            }
+          for (int j0 = 0; j0 < bins; j0 += CH)
+            {
+              double re[CH], im[CH];
+#pragma unroll
+              for (int m = 0; m < CH; ++m) re[m] = im[m] = 0.0;
+#pragma unroll
+              for (int p = 0; p < PMAX; ++p)
+                {
+                  if (p * G.gsize >= ntot) break;
+                  double c = pc[p], sn = ps[p];
+                  const double dc = pdc[p], ds = pds[p];
+#pragma unroll
+                  for (int m = 0; m < CH; ++m)
+                    {
+                      re[m] += c;
+                      im[m] += sn;
+                      const double cn = c * dc - sn * ds;
+                      sn = fma(sn, dc, c * ds);
+                      c = cn;
+                    }
+                  pc[p] = c;
+                  ps[p] = sn;
+                }
+#pragma unroll
+              for (int m = 0; m < CH; ++m)
+                {
+                  const double r = warp_sum(re[m]), q = warp_sum(im[m]);
+                  if (G.lane == 0 && j0 + m < bins)
+                    {
+                      auxw[2 * (j0 + m)] = r;
+                      auxw[2 * (j0 + m) + 1] = q;
+                    }
+                }
+            }
+        }
+      else
       for (int j0 = 0; j0 < bins; j0 += CH)
         {
           double re[CH], im[CH];
 #pragma unroll
           for (int m = 0; m < CH; ++m) re[m] = im[m] = 0.0;
-          const int nsets = (est.setA == est.setB) ? 1 : 2;
           for (int ss = 0; ss < nsets; ++ss)
             {
               const int set = ss == 0 ? est.setA : est.setB;

@@ -56,6 +56,7 @@ struct TripletPass {       // jastrow3bUnDis + potentialThreeBodyUnDis + trimerC
   int setB, setC;          // -1: undistinguishable pass on `set`; else three different sets (LOOP3B_DIS, tools3B.h:25-43)
   double v_R0, v_val;      // F(R) = R<=R0 ? v_val : 0
   double hs_R0;            // hardSphereConstraintThreeBodyUnDis: invalid if any R <= hs_R0
+  double v_thr2, hs_thr2;  // largest R^2 whose correctly rounded sqrt is <= v_R0 / hs_R0 (bit-exact thresholds on R^2)
   RadialFn J;              // may be J_NONE
 };
 
@@ -89,6 +90,10 @@ struct Plan {
   int hist_replicas;
   int needs_pair_table;    // doubles of shared memory reserved per group for the triplet pair tables (0: none)
   int aux_doubles;         // doubles per group for structure-factor partial sums (nwarps*2*bins), set at launch config
+  // cyclic triplet schedule (run_triplet_pass_cyclic, evaluate.cuh): canonical (p, q) offsets modulo trip_mod, every unordered
+  // triplet of a set of trip_mod <= 32 particles exactly once; device pointer, entry = p | q << 8 | symmetric << 16
+  const int *trip_tab;
+  int trip_count, trip_mod;
 };
 
 // DMC run parameters (dmcDriver.cpp:232-255, branching.cpp:5-8)
