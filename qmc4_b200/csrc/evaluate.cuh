@@ -659,39 +659,47 @@ QMC_DEVICE void run_triplet_pass_cyclic(const Plan &plan, const TripletPass &T, 
   G.sync();
   const bool gg = T.J.kind == J_GAUSSGAUSS;
   double se = 0, ser = 0;
-  int npot = 0;
-  for (int t = G.gwarp; t < plan.trip_count; t += G.nwarps)
+  int npot = 0, bad = 0;
+  /* everything the loop needs in registers: the pass constants live in the kernel-parameter bank behind a run-time index */
+  const int jkind = T.J.kind, has_pot = T.has_pot, has_con = T.has_constraint;
+  const double v_thr2 = T.v_thr2, hs_thr2 = T.hs_thr2;
+  double jp[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) jp[k] = T.J.p[k];
+  const int *tabp = plan.trip_tab;
+  const int nent = plan.trip_count, third = M / 3;
+  int ent = G.gwarp < nent ? tabp[G.gwarp] : 0;
+  for (int t = G.gwarp; t < nent; t += G.nwarps)
     {
-      const int ent = plan.trip_tab[t];
       const int p = ent & 255, q = (ent >> 8) & 255, sym = ent >> 16;
-      const bool act = lane < (sym ? M / 3 : M);
+      if (t + G.nwarps < nent) ent = tabp[t + G.nwarps];            /* next entry in flight while this one is worked on */
+      const bool act = lane < (sym ? third : M);
       const int lb = wrap_mod(lane + p, M), lc = wrap_mod(lane + q, M);
       const int ia = p * 32 + lane, ib = (q - p) * 32 + lb, ic = (M - q) * 32 + lc;
+      double R2 = r2t[ia] + r2t[ic] + r2t[ib];
+      R2 = act ? R2 : 0.0;                    /* idle lanes read slots nobody wrote: keep NaN/Inf out of 0 * R2 */
       double w = 0.0;
-      if (act)
+      if (gg)
         {
-          const double R2 = r2t[ia] + r2t[ic] + r2t[ib];
-          if (gg)
-            {
-              const double e = exp_gg(R2, T.J.p);
-              se += e;
-              ser = fma(e, R2, ser);
-              w = e;
-            }
-          else if (T.J.kind != J_NONE)
-            {
-              const double R = sqrt(R2);
-              double d0, d1, d2;
-              eval_radial(T.J, coef, R, d0, d1, d2);
-              w = d1 / R;
-              lp += d0;
-              lap += d2 * 3 + 3 * w * 5;          /* (2D-1) = 5 */
-            }
-          if (T.has_pot && R2 <= T.v_thr2) npot += 1;
-          if (T.has_constraint && R2 <= T.hs_thr2) invalid = 1;
+          double e = exp_gg(R2, jp);
+          e = act ? e : 0.0;
+          se += e;
+          ser = fma(e, R2, ser);
+          w = e;
         }
-      if (T.J.kind != J_NONE)
+      else if (jkind != J_NONE && act)
         {
+          const double R = sqrt(R2);
+          double d0, d1, d2;
+          eval_radial(T.J, coef, R, d0, d1, d2);
+          w = d1 / R;
+          lp += d0;
+          lap += d2 * 3 + 3 * w * 5;          /* (2D-1) = 5 */
+        }
+      npot += (has_pot && act && R2 <= v_thr2) ? 1 : 0;
+      bad |= (has_con && act && R2 <= hs_thr2) ? 1 : 0;
+      if (jkind != J_NONE)
+        { /* three read-modify-writes; within each, the active lanes hit distinct slots */
           if (act) Gw[ia] += w;
           __syncwarp();
           if (act) Gw[ib] += w;
@@ -700,6 +708,7 @@ QMC_DEVICE void run_triplet_pass_cyclic(const Plan &plan, const TripletPass &T, 
           __syncwarp();
         }
     }
+  invalid |= bad;
   if (gg)
     { /* u = u0 e ; u'/R = -2 a u ; 3u'' + 15 u'/R = u0 e (12 a^2 R^2 - 36 a) */
       const double a = T.J.p[0], u0 = T.J.p[1];
