@@ -321,7 +321,7 @@ def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, s
     config = describe(cfgno, cfg, wpg, ngpu, args.scaling, equil, dmc_steps, flushed=not args.no_flush)
     s = parallel.make_comm(lambda comm: System.from_input(cfg, device=local, comm=comm))
     if args.migrate_every or args.migrate_band is not None:
-        s.set_migration(args.migrate_every or 1, 0.01 if args.migrate_band is None else args.migrate_band)
+        s.set_migration(args.migrate_every or 1, 0.02 if args.migrate_band is None else args.migrate_band)
     dofs = s.dofs
     s.upload(initial_walkers(cfg, wpg, 1000 + rank))
 
@@ -363,9 +363,12 @@ def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, s
             # frozen-population check of the IN-STEP migration: with timeStep = 1e-300 a move changes nothing in fp64 and every
             # walker has exactly one descendant, so only the migration moves walkers (unequal start, dead band 0): the global
             # multiset fingerprint must not change while the populations equalise
-            sz = parallel.make_comm(lambda comm: System.from_input(dict(cfg, timeStep=1e-300), device=local, comm=comm))
+            starts = [max(8, min(wpg, 2048) - 37 * r) for r in range(world)]
+            # target population = what is uploaded and a window wider than it: E_T never gets the population-control term
+            sz = parallel.make_comm(lambda comm: System.from_input(dict(cfg, timeStep=1e-300, walkers=sum(starts), delta_walkers=sum(starts)),
+                                                                   device=local, comm=comm))
             sz.set_migration(1, 0.0)
-            nz = max(8, min(wpg, 2048) - 37 * rank)
+            nz = starts[rank]
             sz.upload(initial_walkers(cfg, nz, 5000 + rank))
             sz.step(1, 1)
             fz0 = torch.tensor([int(sz.info("population_checksum"))], dtype=torch.int64, device="cuda")
@@ -380,7 +383,7 @@ def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, s
             sz.close()
             pz = [float(p.item()) for p in pz]
             out["conservation"]["frozen_population_in_step"] = {
-                "start_populations": [max(8, min(wpg, 2048) - 37 * r) for r in range(world)], "end_populations": pz,
+                "start_populations": starts, "end_populations": pz,
                 "walkers_out": float(mz[0].item()), "walkers_in": float(mz[1].item()),
                 "multiset_fingerprint_before": int(fz0.item()) % (1 << 52), "multiset_fingerprint_after": int(fz1.item()) % (1 << 52)}
             fz_ok = (int(fz0.item()) % (1 << 52) == int(fz1.item()) % (1 << 52) and max(pz) - min(pz) <= 1 and mz[0].item() == mz[1].item() > 0)

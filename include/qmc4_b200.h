@@ -254,7 +254,7 @@ int  qmc_rebalance(qmc_ctx *ctx, int64_t *moved);
  * advanced within that step, :133-136): the plan is derived on every rank from the population vector the per-step
  * all-reduce carries, tail walkers travel on a second stream while the move kernel of the next step runs.
  * every: plan every `every` steps (default 1, like the reference).  band: dead band — transfers are posted only when
- * max-min population exceeds band x mean population (default 0.01; 0 = any imbalance, like the reference). */
+ * max-min population exceeds band x mean population (default 0.02; 0 = any imbalance, like the reference). */
 int  qmc_set_migration(qmc_ctx *ctx, int every, double band);
 /* The planner alone (ptools.cpp:93-161), host-side, for tests. */
 int  qmc_plan_rebalance(const int *populations, int nRanks, int *sources, int *amounts);

@@ -143,12 +143,15 @@ struct qmc_ctx {
   double *h_sums = nullptr;         // pinned copy of Ctl::gsum after the last all-reduce: what the migration planner reads
   bool pops_pending = false;        // h_sums holds populations the planner has not looked at yet
   int mig_every = 1;                // plan a migration every mig_every steps ...
-  double mig_band = 0.01;           // ... if max-min population exceeds this fraction of the mean (dead band), min 1 walker
+  double mig_band = 0.02;           // ... if max-min population exceeds this fraction of the mean (dead band), min 1 walker
   long mig_phase = 0, mig_events = 0, mig_out = 0, mig_in = 0;
   int slab_walkers = 0;             // walkers one migration slab holds (bounds a step's transfers)
   bool p2p_connected = false;       // every directed pair of ranks has exchanged a message (NCCL connects lazily: ~140 ms per pair)
   unsigned long long *d_checksum = nullptr;
   // the hot kernel of the one-species / one-pair-pass shapes (kernels_pair.cu) replaces the general move kernel when the plan allows
+  ScanWorkspace scan_ws = {};
+  int *scan_ws_i = nullptr;
+  double *scan_ws_d = nullptr;
   bool trip_cyclic = false;
   int trip_mod = 0;
   int *trip_tab = nullptr;
@@ -802,6 +805,7 @@ StepArgs make_step_args(qmc_ctx *c, int accumulate)
   a.hist = (accumulate && c->has_hist) ? c->hist : nullptr;
   a.accumulate = accumulate;
   a.cap = (int)c->cap;
+  a.ws = c->scan_ws;
   return a;
 }
 
@@ -1243,6 +1247,8 @@ void qmc_destroy(qmc_ctx *c)
   cudaFree(c->d_checksum);
   cudaFree(c->lean_tab);
   cudaFree(c->trip_tab);
+  cudaFree(c->scan_ws_i);
+  cudaFree(c->scan_ws_d);
   if (c->h_sums) cudaFreeHost(c->h_sums);
   if (c->ev_scan) cudaEventDestroy(c->ev_scan);
   if (c->ev_ar) cudaEventDestroy(c->ev_ar);
@@ -1497,6 +1503,18 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
       CK(cudaMemset(c->flags, 0, capacity * 4));
     }
   CK(cudaMalloc(&c->d_checksum, 8));
+  {
+    const int nb = scan_max_blocks();
+    CK(cudaMalloc(&c->scan_ws_i, (size_t)(2 + 3 * nb) * sizeof(int)));
+    CK(cudaMemset(c->scan_ws_i, 0, (size_t)(2 + 3 * nb) * sizeof(int)));
+    CK(cudaMalloc(&c->scan_ws_d, (size_t)nb * sizeof(double)));
+    c->scan_ws.ticket = c->scan_ws_i;
+    c->scan_ws.done = c->scan_ws_i + 1;
+    c->scan_ws.total = c->scan_ws_i + 2;
+    c->scan_ws.nacc = c->scan_ws_i + 2 + nb;
+    c->scan_ws.flag = reinterpret_cast<unsigned *>(c->scan_ws_i + 2 + 2 * nb);
+    c->scan_ws.esum = c->scan_ws_d;
+  }
   c->cfg.grid = grid_for(c, capacity);
   {
     const Plan &P = c->plan;

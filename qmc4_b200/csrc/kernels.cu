@@ -7,9 +7,7 @@
 //        -> log Green ratio (dmcMoves.cpp:32-57) + Metropolis (metropolis.cpp:5-29, dmcDriver.cpp:27-38)
 //        -> accept / reject (dmcDriver.cpp:56-84) -> nDescendants (branching.cpp:11-14)
 //        -> estimators on sampling steps.
-//   scan_kernel      : exclusive prefix sum of nDescendants -> parent map of the next step,
-//                      new population, sum of energies -> E_T (branching.cpp:65-97), block
-//                      accumulators.  Population and E_T never leave the device.
+//   (the branching scan shared by both pipelines lives in kernels_scan.cu)
 //   eval_kernel      : evaluation of given configurations (parity entry, initial population,
 //                      estimator accumulation over given configurations).
 #include <algorithm>
@@ -251,149 +249,6 @@ propagate_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Branching bookkeeping, single CTA of 1024 threads.  Walkers are consumed in tiles of 4096 with
-// coalesced 16-byte loads (4 consecutive walkers per thread), an in-register prefix over the 4, a
-// shuffle scan inside each warp and a 32-entry scan of the warp totals; a running carry links the
-// tiles.  All floating-point sums are combined in a fixed order (deterministic).
-constexpr int SCAN_THREADS = 1024;
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, int *parent_next, int n_partials, int multi_rank, int init_mode)
-{
-  __shared__ int s_warp[32];
-  __shared__ double s_e[SCAN_THREADS], s_mv[SCAN_THREADS], s_ac[SCAN_THREADS];
-  __shared__ int s_carry, s_tile;
-  Ctl *ctl = a.ctl;
-  const int W = ctl->n_cur;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (t == 0) s_carry = 0;
-  __syncthreads();
-  double esum = 0;
-  int dropped = 0;
-  for (int base = 0; base < W; base += 4 * SCAN_THREADS)
-    {
-      const int j0 = base + 4 * t;
-      int n[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) n[u] = (j0 + u < W) ? a.n_desc[j0 + u] : 0;
-      const int mine = n[0] + n[1] + n[2] + n[3];
-      int inc = mine;                                   /* inclusive scan inside the warp */
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
-        {
-          const int v = __shfl_up_sync(0xffffffffu, inc, d);
-          if (lane >= d) inc += v;
-        }
-      if (lane == 31) s_warp[warp] = inc;
-      __syncthreads();
-      if (warp == 0)
-        {
-          int w = s_warp[lane], wi = w;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1)
-            {
-              const int v = __shfl_up_sync(0xffffffffu, wi, d);
-              if (lane >= d) wi += v;
-            }
-          s_warp[lane] = wi - w;                        /* exclusive offsets of the warps */
-          if (lane == 31) s_tile = wi;                  /* tile total */
-        }
-      __syncthreads();
-      int off = s_carry + s_warp[warp] + (inc - mine);
-      const int tile_total = s_tile;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        {
-          const int j = j0 + u;
-          if (n[u] > 0)
-            {
-              const double e = a.out.E[j];
-              for (int c = 0; c < n[u]; ++c)
-                {
-                  if (off < a.cap)
-                    {
-                      parent_next[off] = j;
-                      esum += e;
-                    }
-                  else dropped = 1;
-                  ++off;
-                }
-            }
-        }
-      __syncthreads();
-      if (t == 0) s_carry += tile_total;
-      __syncthreads();
-    }
-  int total = s_carry;
-  if (total == 0 && W > 0)
-    { /* always keep at least a walker (branching.cpp:29-32) */
-      if (t == 0)
-        {
-          a.n_desc[0] = 1;
-          parent_next[0] = 0;
-          esum = a.out.E[0];
-        }
-      total = 1;
-    }
-  if (dropped) ctl->overflow = 1;
-  // fixed-order tree sums: energies, metropolis counters (per-group partials)
-  {
-    double mv = 0, ac = 0;
-    for (int i = t; i < n_partials; i += SCAN_THREADS)
-      {
-        mv += a.partials[2 * i];
-        ac += a.partials[2 * i + 1];
-      }
-    s_e[t] = esum;
-    s_mv[t] = mv;
-    s_ac[t] = ac;
-  }
-  __syncthreads();
-  for (int d = SCAN_THREADS / 2; d >= 1; d >>= 1)
-    {
-      if (t < d)
-        {
-          s_e[t] += s_e[t + d];
-          s_mv[t] += s_mv[t + d];
-          s_ac[t] += s_ac[t + d];
-        }
-      __syncthreads();
-    }
-  if (t == 0)
-    {
-      const int newW = min(total, a.cap);
-      const double moves = s_mv[0], acc = s_ac[0];
-      ctl->n_prev = W;
-      ctl->n_cur = newW;
-      if (!init_mode)
-        {
-          ctl->step += 1;
-          ctl->blk_moves += moves;
-          ctl->blk_acc += acc;
-          ctl->blk_steps += 1;
-        }
-      ctl->lsum[0] = s_e[0];
-      ctl->lsum[1] = (double)newW;
-      for (int r = 0; r < MAX_RANKS; ++r)
-        {
-          ctl->lsum[2 + r] = (r == dmc.rank) ? (double)newW : 0.0;
-          ctl->lsum[2 + MAX_RANKS + r] = (r == dmc.rank) ? (double)(a.cap - max(W, newW)) : 0.0;
-        }
-      if (a.accumulate)
-        {
-          ctl->blk_esum += s_e[0];
-          ctl->blk_ecount += (double)newW;
-          ctl->est_weight += (double)newW;
-        }
-      if (!multi_rank)
-        {
-          for (int r = 0; r < NSUM; ++r) ctl->gsum[r] = ctl->lsum[r];
-          if (dmc.branching_on) ctl->eshift = branch_shift(dmc, s_e[0], (double)newW);
-        }
-    }
-}
-
 __global__ void finalize_shift_kernel(const __grid_constant__ DmcParams dmc, Ctl *ctl)
 {
   if (threadIdx.x == 0 && blockIdx.x == 0 && dmc.branching_on) ctl->eshift = branch_shift(dmc, ctl->gsum[0], ctl->gsum[1]);
@@ -593,14 +448,6 @@ cudaError_t launch_propagate(int ksel, bool hist, const LaunchCfg &cfg, cudaStre
   size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
   void *args[] = {(void *)&plan, (void *)&dmc, (void *)&a, (void *)&nw, (void *)&gb};
   return cudaLaunchKernel(prop_ptr(ksel, hist), dim3(cfg.grid), dim3(cfg.block), args, cfg.smem, st);
-}
-
-cudaError_t launch_scan(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, int n_partials, int multi_rank, int init_mode)
-{
-  // the parent map written here is consumed by the NEXT propagate; it lives behind a.parent's twin
-  int *parent_next = a.parent;
-  QMC_LAUNCH(scan_kernel, 1, SCAN_THREADS, 0, st, dmc, a, parent_next, n_partials, multi_rank, init_mode);
-  return cudaGetLastError();
 }
 
 cudaError_t launch_finalize_shift(cudaStream_t st, const DmcParams &dmc, Ctl *ctl)

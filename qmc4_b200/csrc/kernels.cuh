@@ -53,6 +53,14 @@ struct TraceDev {              // optional per-walker trace (device pointers, ma
   int *accepted, *valid, *n_desc, *parent;
 };
 
+// inter-CTA workspace of the branching scan (kernels_scan.cu); zero between launches (the kernel resets it)
+struct ScanWorkspace {
+  int *ticket, *done;          // arrival / completion counters
+  int *total, *nacc;           // per CTA: descendants of its range, accepted moves
+  unsigned *flag;              // per CTA: total published
+  double *esum;                // per CTA: sum of the energies of its descendants
+};
+
 struct StepArgs {
   WalkerBuf in, out;
   int *parent;                 // [cap] source slot in `in` for each slot of `out` (rewritten by the scan)
@@ -68,6 +76,7 @@ struct StepArgs {
   int *flags;                  // [cap] bit 0: move accepted (the scan counts the Metropolis statistics from these)
   int first, count;            // move kernel: walkers [first, first+count); count < 0: [0, ctl->n_cur).  first = -1 - d: ctl->n_cur - d
   int n_adjust;                // scan: population moved this step = ctl->n_cur + n_adjust (arrivals - departures of the migration)
+  ScanWorkspace ws;
 };
 
 struct EvalArgs {
@@ -93,6 +102,7 @@ cudaError_t launch_eval(int ksel, bool hist, const LaunchCfg &cfg, cudaStream_t 
 cudaError_t launch_propagate(int ksel, bool hist, const LaunchCfg &cfg, cudaStream_t st, const Plan &plan,
                              const DmcParams &dmc, const StepArgs &a);
 cudaError_t launch_scan(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, int n_partials, int multi_rank, int init_mode);
+int scan_max_blocks();
 cudaError_t launch_finalize_shift(cudaStream_t st, const DmcParams &dmc, Ctl *ctl);
 cudaError_t launch_init_identity(cudaStream_t st, int *parent, int *n_desc, int n, Ctl *ctl);
 cudaError_t launch_reduce_hist(cudaStream_t st, const double *hist, int replicas, int stride, double *out);

@@ -138,153 +138,6 @@ move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams
     }
 }
 
-constexpr int SCAN2_THREADS = 1024;
-
-// scan_kernel of pipeline 1 + the branching decision (nDescendants) it used to receive from propagate.
-__global__ void __launch_bounds__(SCAN2_THREADS)
-scan_v2_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const double *e_old, int *parent_next, int multi_rank)
-{
-  __shared__ int s_warp[32];
-  __shared__ double s_e[SCAN2_THREADS], s_mv[SCAN2_THREADS], s_ac[SCAN2_THREADS];
-  __shared__ int s_carry, s_tile;
-  Ctl *ctl = a.ctl;
-  const int W = ctl->n_cur + a.n_adjust;     /* walkers moved this step: migration removed the tail / appended the arrivals */
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const unsigned long long step = ctl->step;
-  const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
-  const double eT = dmc.branching_on ? branch_shift(dmc, ctl->gsum[0], ctl->gsum[1]) : 0.0;
-  if (t == 0) s_carry = 0;
-  __syncthreads();
-  double esum = 0;
-  int dropped = 0, nacc = 0;
-  for (int base = 0; base < W; base += 4 * SCAN2_THREADS)
-    {
-      const int j0 = base + 4 * t;
-      int n[4];
-      double e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        {
-          const int j = j0 + u;
-          n[u] = 0;
-          e[u] = 0;
-          if (j < W)
-            {
-              e[u] = a.out.E[j];
-              nacc += a.flags[j] & 1;
-              int nn = 1;
-              if (dmc.branching_on || a.trace.u_b)
-                {
-                  const u32x4 rd = philox4x32_10({(uint32_t)j, 0xffffffffu, step_lo, step_hi}, dmc.seed_lo, dmc.seed_hi);
-                  const double u_b = u01_53(rd.z, rd.w);
-                  if (dmc.branching_on) nn = (int)(exp(-dmc.tau * (0.5 * (e[u] + e_old[j]) - eT)) + u_b);      /* branching.cpp:13 */
-                  if (a.trace.u_b) a.trace.u_b[j] = u_b;
-                }
-              n[u] = max(0, min(nn, a.cap));
-              a.n_desc[j] = n[u];
-              if (a.trace.n_desc) a.trace.n_desc[j] = n[u];
-            }
-        }
-      const int mine = n[0] + n[1] + n[2] + n[3];
-      int inc = mine;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
-        {
-          const int v = __shfl_up_sync(0xffffffffu, inc, d);
-          if (lane >= d) inc += v;
-        }
-      if (lane == 31) s_warp[warp] = inc;
-      __syncthreads();
-      if (warp == 0)
-        {
-          int w = s_warp[lane], wi = w;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1)
-            {
-              const int v = __shfl_up_sync(0xffffffffu, wi, d);
-              if (lane >= d) wi += v;
-            }
-          s_warp[lane] = wi - w;
-          if (lane == 31) s_tile = wi;
-        }
-      __syncthreads();
-      int off = s_carry + s_warp[warp] + (inc - mine);
-      const int tile_total = s_tile;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        {
-          const int j = j0 + u;
-          for (int c = 0; c < n[u]; ++c)
-            {
-              if (off < a.cap)
-                {
-                  parent_next[off] = j;
-                  esum += e[u];
-                }
-              else dropped = 1;
-              ++off;
-            }
-        }
-      __syncthreads();
-      if (t == 0) s_carry += tile_total;
-      __syncthreads();
-    }
-  int total = s_carry;
-  if (total == 0 && W > 0)
-    {
-      if (t == 0)
-        {
-          a.n_desc[0] = 1;
-          parent_next[0] = 0;
-          esum = a.out.E[0];
-        }
-      total = 1;
-    }
-  if (dropped) ctl->overflow = 1;
-  s_e[t] = esum;
-  s_mv[t] = 0;
-  s_ac[t] = (double)nacc;      /* small integers: exact in any order */
-  __syncthreads();
-  for (int d = SCAN2_THREADS / 2; d >= 1; d >>= 1)
-    {
-      if (t < d)
-        {
-          s_e[t] += s_e[t + d];
-          s_mv[t] += s_mv[t + d];
-          s_ac[t] += s_ac[t + d];
-        }
-      __syncthreads();
-    }
-  if (t == 0)
-    {
-      const int newW = min(total, a.cap);
-      ctl->n_prev = W;
-      ctl->n_cur = newW;
-      ctl->step += 1;
-      ctl->blk_moves += (double)W;
-      ctl->blk_acc += s_ac[0];
-      ctl->blk_steps += 1;
-      ctl->lsum[0] = s_e[0];
-      ctl->lsum[1] = (double)newW;
-      for (int r = 0; r < MAX_RANKS; ++r)
-        {
-          ctl->lsum[2 + r] = (r == dmc.rank) ? (double)newW : 0.0;
-          ctl->lsum[2 + MAX_RANKS + r] = (r == dmc.rank) ? (double)(a.cap - max(W, newW)) : 0.0;
-        }
-      if (a.accumulate)
-        {
-          ctl->blk_esum += s_e[0];
-          ctl->blk_ecount += (double)newW;
-          ctl->est_weight += (double)newW;
-        }
-      if (!multi_rank)
-        {
-          for (int r = 0; r < NSUM; ++r) ctl->gsum[r] = ctl->lsum[r];
-          if (dmc.branching_on) ctl->eshift = branch_shift(dmc, s_e[0], (double)newW);
-        }
-    }
-}
-
 // Estimators over the post-branching population with unit weight per walker (dmcDriver::accumulate,
 // dmcDriver.cpp:257-264): slot j of the new population is walker parent[j] of `buf`.
 // MINB: resident CTAs per SM the register allocation is bounded for (2: up to 128 registers, 3: 80, 4: 64) — the
@@ -453,12 +306,6 @@ cudaError_t launch_propagate_v2(int ksel, const LaunchCfg &cfg, int grid, cudaSt
   size_t gb = (cfg.smem - (size_t)plan.hist_stride * 8) / cfg.groups_per_cta;
   void *args[] = {(void *)&plan, (void *)&dmc, (void *)&a, (void *)&e_old, (void *)&nw, (void *)&gb};
   return cudaLaunchKernel(prop2_ptr(ksel), dim3(grid), dim3(cfg.block), args, cfg.smem, st);
-}
-
-cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs &a, const double *e_old, int multi_rank)
-{
-  QMC_LAUNCH(scan_v2_kernel, 1, SCAN2_THREADS, 0, st, dmc, a, e_old, a.parent, multi_rank);
-  return cudaGetLastError();
 }
 
 cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const WalkerBuf &buf, const int *parent,

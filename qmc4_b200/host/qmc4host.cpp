@@ -474,7 +474,9 @@ void dmcDriver::out(size_t iBlock)
   if (r.overflow != 0) throw invalidState("walker population exceeded the device buffer capacity");
   for (auto *e : estimators) e->collect(ctx, r);
   int64_t moved = 0;
-  if (nranks > 1) check(qmc_rebalance(ctx, &moved));        /* walkerLoadBalancer (dmcDriver.cpp:150-157), once per block */
+  /* walkers migrate inside qmc_step, one step late (dmcDriver.cpp:112,150-157); this synchronous pass at the block boundary
+     evens out what the dead band left and is the path that carries forward-walking records along */
+  if (nranks > 1) check(qmc_rebalance(ctx, &moved));
   if (master)
     {
       energyEst->collect(ctx, r);

@@ -360,7 +360,7 @@ class System:
         self._ck(self.lib.qmc_rebalance(self.ctx, C.byref(m)))
         return m.value
 
-    def set_migration(self, every=1, band=0.01):
+    def set_migration(self, every=1, band=0.02):
         """in-step walker migration of qmc_step: plan every `every` steps, dead band `band` x mean population"""
         self._ck(self.lib.qmc_set_migration(self.ctx, int(every), float(band)))
 

@@ -156,6 +156,7 @@ static inline void emu_sincosf(float x, float *s, float *c)
 #define __log2f emu_log2f     /* glibc owns the reserved names */
 #define __sincosf emu_sincosf
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 
 using std::max;
