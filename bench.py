@@ -166,6 +166,11 @@ def cpu_reference_arm(cfg, seconds_budget, max_procs=None):
         cores = min(cores, max_procs)
     N = sum(cfg["N"])
     pairs, trip, _, _ = work_per_move(cfg)
+    dropped = ""
+    if any(m.get("kind") == "structureFactor" for m in cfg.get("measurements", [])):
+        # the reference builds structureFactor for DIMENSIONS == 1 only (structureFactor.h:8): its CPU sample runs without it
+        cfg = dict(cfg, measurements=[m for m in cfg["measurements"] if m.get("kind") != "structureFactor"])
+        dropped = "; structureFactor measurement dropped (the reference builds it in 1-D only)"
     if os.path.exists(orc.REF_BIN):
         est_us = 0.12 * (pairs + 6 * trip) + 25.0 * N / 10 + 5           # planning estimate per walker-move
         w_cpu, per_walker = cpu_sample_shape(cfg)
@@ -206,7 +211,7 @@ def cpu_reference_arm(cfg, seconds_budget, max_procs=None):
             rate += mv / (ms * 1e-3)
         wall = time.time() - t0
         return {"value": rate, "unit": "walker-moves/s", "cores": cores, "kind": "reference",
-                "sample": "%d procs x %d walkers x %d steps of the same input.json (seed+core), reference timers totalRunningTime-outputTime; wall %.1fs" % (cores, w_cpu, spb * 4, wall),
+                "sample": "%d procs x %d walkers x %d steps of the same input.json (seed+core), reference timers totalRunningTime-outputTime; wall %.1fs%s" % (cores, w_cpu, spb * 4, wall, dropped),
                 "pair_evals_per_s": rate * pairs}
     port = orc.Port()
     nW = 32
@@ -249,7 +254,11 @@ def measure(s, cfg, cfgno, steps, warmup, dmc_steps, equil, flush, barrier, worl
         s.step(dmc_steps, 1)
     s.block_results()
     s.info("propagate_timers_reset")
-    s.info("time_kernels_on")
+    # launch-bound shape (config 1: two ~10 us kernels per DMC step): the timed region replays CUDA graphs of step pairs, which
+    # per-launch event pairs would prevent; the move kernel is timed in a separate pass right after the timed region instead
+    separate_timing = cfgno == 1
+    if not separate_timing:
+        s.info("time_kernels_on")
     l0 = s.info("launches")
     m0 = (s.info("migration_events"), s.info("migrated_out"), s.info("migrated_in"))
     if sampler is not None:
@@ -264,6 +273,11 @@ def measure(s, cfg, cfgno, steps, warmup, dmc_steps, equil, flush, barrier, worl
     b = s.block_results()                       # n_moves etc. are global (all-reduced) with a communicator
     clocks = sampler.stop() if sampler is not None else None
     launches = s.info("launches") - l0
+    graph_replays = s.info("graph_replays")
+    if separate_timing:
+        s.info("time_kernels_on")
+        s.step(min(dmc_steps, 200), 1)
+        s.block_results()
     prop_ms = s.info("propagate_ms_total") / max(1.0, s.info("propagate_launches_timed"))
     s.info("time_kernels_off")
     ms_total = b["device_ms"]
@@ -281,6 +295,7 @@ def measure(s, cfg, cfgno, steps, warmup, dmc_steps, equil, flush, barrier, worl
            "population": local_pop, "acceptance": b["n_accepted"] / max(b["n_moves"], 1),
            "energy_per_particle": b["energy_sum"] / max(b["energy_count"], 1) / sum(cfg["N"]), "launches": int(launches),
            "prop_ms": prop_ms, "achieved_tflops": achieved, "moves_per_launch": moves_per_launch, "clocks": clocks,
+           "graph_replays": graph_replays, "launch_timing": "separate pass after the timed region" if separate_timing else "event pairs inside the timed region",
            "pair_evals_per_s": value * pairs, "triplet_evals_per_s": value * trip,
            "migration": {"events": s.info("migration_events") - m0[0], "walkers_out": s.info("migrated_out") - m0[1],
                          "walkers_in": s.info("migrated_in") - m0[2], "every": s.info("migrate_every"), "band": s.info("migrate_band")}}
@@ -293,7 +308,7 @@ def roofline_block(s, cfg, cfgno, m, peak, hbm_peak):
     r = {"bound": "fp64" if cfgno != 1 else "hbm", "kernel": "move_kernel (drift-diffusion + pair/triplet evaluation + Green ratio + Metropolis)",
          "achieved": m["achieved_tflops"], "peak": peak, "unit": "TFLOP/s",
          "frac": (m["achieved_tflops"] / peak) if (peak and m["achieved_tflops"]) else None, "traffic": load_traffic(cfgno),
-         "algorithmic_flop_per_launch": m["moves_per_launch"] * flops_per_move, "avg_launch_ms": m["prop_ms"],
+         "algorithmic_flop_per_launch": m["moves_per_launch"] * flops_per_move, "avg_launch_ms": m["prop_ms"], "launch_timing": m["launch_timing"],
          "flop_per_pair": FLOP_PER_PAIR, "flop_per_coordinate": FLOP_PER_COORD, "flop_per_triplet": FLOP_PER_TRIPLET,
          "peak_source": "FP64 DFMA pipe measured in-process (qmc_get_info fp64_peak_tflops: 8 independent DFMA chains/thread, 148x8 CTAs); "
                         "MEASURED_PEAKS.json carries HBM and bf16 only",
@@ -307,7 +322,7 @@ def roofline_block(s, cfg, cfgno, m, peak, hbm_peak):
     return r
 
 
-def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, steps, warmup, primary):
+def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, steps, warmup, primary, method=None):
     ngpu = max(args.gpus, world)
     dmc_steps = args.dmc_steps or DMC_STEPS_PER_STEP[cfgno]
     if args.scaling == "strong":
@@ -318,7 +333,10 @@ def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, s
         wpg = args.walkers
     equil = args.equil if primary else min(args.equil, 100)
     cfg = workload(cfgno, wpg, ngpu)
+    if method:
+        cfg["method"] = method          # "svmc": the same walkers without branching (main.cpp:393-395)
     config = describe(cfgno, cfg, wpg, ngpu, args.scaling, equil, dmc_steps, flushed=not args.no_flush)
+    config["method"] = cfg["method"]
     s = parallel.make_comm(lambda comm: System.from_input(cfg, device=local, comm=comm))
     if args.migrate_every or args.migrate_band is not None:
         s.set_migration(args.migrate_every or 1, 0.02 if args.migrate_band is None else args.migrate_band)
@@ -424,8 +442,11 @@ def run_config(cfgno, args, torch, dist, parallel, System, rank, world, local, s
                       "d2h_bytes_per_step": int(nW * (dofs + 1) * 8 + 72),
                       "note": "per bench step: qmc_upload_walkers(pinned host R) [+ initial evaluation] -> qmc_step(%d DMC steps) -> qmc_block_results -> qmc_download_walkers(host R,E)" % dmc_steps}
     if rank == 0:
-        out["kernel"] = {"warps_per_walker": s.info("warps_per_walker"), "grid": s.info("grid"), "smem_bytes": s.info("smem_bytes"),
-                         "regs": s.info("regs_propagate"), "variant": s.info("kernel_variant"), "pipeline": s.info("pipeline")}
+        out["kernel"] = {"move_kernel": "pair_move_kernel (kernels_pair.cu)" if s.info("pair_kernel") else
+                         "small_move_kernel (kernels_small.cu, %d walkers per warp)" % s.info("small_walkers_per_warp") if s.info("small_kernel") else
+                         "move_kernel (kernels_v2.cu)", "grid": s.info("grid"), "smem_bytes": s.info("smem_bytes"),
+                         "regs": s.info("regs_propagate"), "pipeline": s.info("pipeline"),
+                         "warps_per_walker": s.info("pair_kernel_warps_per_walker") if s.info("pair_kernel") else s.info("warps_per_walker")}
         if primary:
             out["peak"] = s.info("fp64_peak_tflops")
     s.close()
@@ -509,19 +530,21 @@ def main():
     if world == 1 and not args.no_secondary and args.config == DEFAULT_CONFIG:
         # the other BASELINE shapes, same measurement on smaller samples (N=1 only; parity for them is in tests/)
         sec = {}
-        for c2 in (2, 3, 4, 1):
+        for c2, meth in ((2, None), (3, None), (4, None), (1, None), (1, "svmc")):
+            key = "config%d" % c2 + ("_" + meth if meth else "")
             try:
-                r2 = run_config(c2, args, torch, dist, parallel, System, rank, world, local, max(3, min(steps, 5)), 3, primary=False)
+                r2 = run_config(c2, args, torch, dist, parallel, System, rank, world, local, max(3, min(steps, 5)), 3, primary=False, method=meth)
                 m2 = r2["m"]
                 rf = roofline_block(None, r2["cfg"], c2, m2, peak, hbm_peak)
-                sec["config%d" % c2] = {"config": r2["config"], "value": m2["value"], "unit": "walker-moves/s", "ms_per_step": m2["ms_per_step"],
+                sec[key] = {"config": r2["config"], "value": m2["value"], "unit": "walker-moves/s", "ms_per_step": m2["ms_per_step"],
                                         "ms_per_dmc_step": m2["ms_per_dmc_step"], "pair_evals_per_s": m2["pair_evals_per_s"],
                                         "triplet_evals_per_s": m2["triplet_evals_per_s"], "acceptance": m2["acceptance"],
-                                        "population": m2["population"], "gpu_launches": m2["launches"], "roofline": rf, "kernel": r2["kernel"]}
+                                        "population": m2["population"], "gpu_launches": m2["launches"], "cuda_graph_replays": m2["graph_replays"],
+                                        "roofline": rf, "kernel": r2["kernel"]}
                 if not args.no_cpu_baseline:
-                    sec["config%d" % c2]["cpu_baseline"] = cpu_reference_arm(r2["cfg"], seconds_budget=4.0)
+                    sec[key]["cpu_baseline"] = cpu_reference_arm(r2["cfg"], seconds_budget=4.0)
             except Exception as e:          # a secondary shape must never take the headline down
-                sec["config%d" % c2] = {"error": repr(e)[:300]}
+                sec[key] = {"error": repr(e)[:300]}
         line["secondary"] = sec
     if not args.no_cpu_baseline and world == 1:          # rank 0 at N=1 only (the N>1 runs compare against the same number)
         line["cpu_baseline"] = cpu_reference_arm(cfg, seconds_budget=12.0)

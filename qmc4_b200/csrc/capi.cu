@@ -152,6 +152,16 @@ struct qmc_ctx {
   ScanWorkspace scan_ws = {};
   int *scan_ws_i = nullptr;
   double *scan_ws_d = nullptr;
+  // CUDA graph of two consecutive steps (the walker buffers ping-pong, so two steps restore the launch arguments): single rank,
+  // every step a sampling step, no per-launch timers.  Replayed nSteps/2 times by qmc_step (QMC4_GRAPHS=0 disables).
+#ifndef QMC_EMULATE
+  cudaGraphExec_t step_graph = nullptr;
+#endif
+  bool use_graphs = true;
+  long graph_launches_per_replay = 0;
+  long graph_replays = 0;
+  bool small = false;               // kernels_small.cu: several walkers per warp (one species, N <= 16, no triplet terms)
+  int small_grid = 0;
   bool trip_cyclic = false;
   int trip_mod = 0;
   int *trip_tab = nullptr;
@@ -932,6 +942,7 @@ int one_step_v2(qmc_ctx *c, int accumulate, const TraceDev *tr)
   const bool timed = c->time_kernels && c->pev_used < qmc_ctx::NEV;
   if (timed) CK(cudaEventRecord(c->pev0[c->pev_used], c->stream));
   if (c->lean) CK(launch_pair_move(c->lean_vk, c->lean_occ, c->lean_cfg, c->lean_cfg.grid, c->stream, c->plan, c->dmc, c->lean_tab, a, c->e_old));
+  else if (c->small) CK(launch_small_move(c->plan.N[0], c->small_grid, c->stream, c->plan, c->dmc, a, c->e_old));
   else CK(launch_propagate_v2(c->ksel, c->cfg, c->cfg.grid, c->stream, c->plan, c->dmc, a, c->e_old));
   if (timed) CK(cudaEventRecord(c->pev1[c->pev_used++], c->stream));
   if (T) CK(cudaEventRecord(T->m1, c->stream));
@@ -972,6 +983,11 @@ int one_step_v2(qmc_ctx *c, int accumulate, const TraceDev *tr)
                   const LaunchCfg &K = c->lean ? c->lean_cfg : c->cfg;
                   const int g = std::max(1, std::min(K.grid, (n_recv + K.groups_per_cta - 1) / K.groups_per_cta));
                   if (c->lean) CK(launch_pair_move(c->lean_vk, c->lean_occ, K, g, c->stream, c->plan, c->dmc, c->lean_tab, t, c->e_old));
+                  else if (c->small)
+                    {
+                      const int wpc = small_walkers_per_cta(c->plan.N[0]);
+                      CK(launch_small_move(c->plan.N[0], std::max(1, std::min(c->small_grid, (n_recv + wpc - 1) / wpc)), c->stream, c->plan, c->dmc, t, c->e_old));
+                    }
                   else CK(launch_propagate_v2(c->ksel, c->cfg, g, c->stream, c->plan, c->dmc, t, c->e_old));
                   c->launches += 1;
                 }
@@ -1219,6 +1235,8 @@ int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, co
           cudaEventCreate(&t.a1);
         }
     }
+  if (const char *v = getenv("QMC4_GRAPHS"))
+    c->use_graphs = atoi(v) != 0;
   if (const char *v = getenv("QMC4_MIGRATE_EVERY"))
     c->mig_every = std::max(1, atoi(v));
   if (const char *v = getenv("QMC4_MIGRATE_BAND"))
@@ -1246,6 +1264,9 @@ void qmc_destroy(qmc_ctx *c)
   cudaFree(c->flags);
   cudaFree(c->d_checksum);
   cudaFree(c->lean_tab);
+#ifndef QMC_EMULATE
+  if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+#endif
   cudaFree(c->trip_tab);
   cudaFree(c->scan_ws_i);
   cudaFree(c->scan_ws_d);
@@ -1547,6 +1568,19 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
             CK(cudaMalloc(&c->lean_tab, sizeof tab));
             CK(cudaMemcpy(c->lean_tab, tab, sizeof tab, cudaMemcpyHostToDevice));
           }
+      }
+  }
+  {
+    const Plan &P = c->plan;
+    const char *se = getenv("QMC4_SMALL");
+    bool ok = c->pipeline == 2 && !c->lean && !(se && atoi(se) == 0) && P.nSpecies == 1 && P.N[0] <= 16 && P.n3b == 0;
+    for (int t = 0; t < P.n2b; ++t) ok = ok && P.p2[t].setA == 0 && P.p2[t].setB == 0;
+    c->small = ok;
+    if (ok)
+      {
+        const int wpc = small_walkers_per_cta(P.N[0]);
+        const int64_t want = (capacity + wpc - 1) / wpc;
+        c->small_grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sms * small_move_occupancy(P.N[0])));
       }
   }
   c->n_partials = c->cfg.grid * c->cfg.groups_per_cta;
@@ -1867,7 +1901,41 @@ int qmc_step(qmc_ctx *c, int nSteps, int sampleEvery)
   const double h0 = c->trace_n ? host_now_ms() : 0.0;
   c->trace_used = 0;
   CK(cudaEventRecord(c->ev0, c->stream));
-  for (int k = 0; k < nSteps; ++k)
+  int k0 = 0;
+#ifndef QMC_EMULATE
+  if (c->use_graphs && c->pipeline == 2 && c->nranks == 1 && sampleEvery == 1 && !c->time_kernels && !c->trace_n && !c->genealogy() &&
+      !c->force_energy && nSteps >= 4)
+    { /* launch-bound regime (config 1: two 10 us kernels per step): replay a captured pair of steps */
+      if (c->cur == 1)
+        { /* the graph was captured from buffer 0 */
+          c->sample_phase += 1;
+          if (one_step(c, 1, nullptr)) return 1;
+          k0 = 1;
+        }
+      if (!c->step_graph)
+        {
+          cudaGraph_t g = nullptr;
+          const long l0 = c->launches;
+          CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+          int rc = one_step(c, 1, nullptr);
+          if (!rc) rc = one_step(c, 1, nullptr);
+          cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+          if (rc || e != cudaSuccess) return fail(c, std::string("graph capture of the step pair failed: ") + (rc ? c->err : cudaGetErrorString(e)));
+          c->graph_launches_per_replay = c->launches - l0;
+          c->launches = l0;                      /* nothing ran during the capture */
+          CK(cudaGraphInstantiate(&c->step_graph, g, 0));
+          cudaGraphDestroy(g);
+        }
+      for (; k0 + 2 <= nSteps; k0 += 2)
+        {
+          CK(cudaGraphLaunch(c->step_graph, c->stream));
+          c->sample_phase += 2;
+          c->launches += c->graph_launches_per_replay;
+          c->graph_replays += 1;
+        }
+    }
+#endif
+  for (int k = k0; k < nSteps; ++k)
     {
       c->sample_phase += 1;
       const int accumulate = (c->sample_phase % sampleEvery) == 0;
@@ -2466,7 +2534,7 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "log_up") *value = c->dmc.log_up;
   else if (k == "log_down") *value = c->dmc.log_down;
   else if (k == "capacity") *value = (double)c->cap;
-  else if (k == "grid") *value = c->lean ? c->lean_cfg.grid : c->cfg.grid;
+  else if (k == "grid") *value = c->lean ? c->lean_cfg.grid : c->small ? c->small_grid : c->cfg.grid;
   else if (k == "estimator_grid") *value = c->est_grid;
   else if (k == "estimator_occupancy_target") *value = c->est_occ;
   else if (k == "block") *value = c->cfg.block;
@@ -2476,6 +2544,9 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "kernel_variant") *value = c->ksel;
   else if (k == "pipeline") *value = c->pipeline;
   else if (k == "pair_kernel") *value = c->lean ? 1 : 0;
+  else if (k == "graph_replays") *value = (double)c->graph_replays;
+  else if (k == "small_kernel") *value = c->small ? 1 : 0;
+  else if (k == "small_walkers_per_warp") *value = c->small ? 32 / small_segment_width(c->plan.N[0]) : 0;
   else if (k == "triplet_cyclic") *value = c->trip_cyclic ? 1 : 0;
   else if (k == "triplet_table_entries") *value = c->plan.trip_count;
   else if (k == "pair_kernel_occupancy_target") *value = c->lean_occ;
@@ -2499,7 +2570,7 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "ctas_per_sm") *value = propagate_occupancy(c->ksel, c->has_hist, c->cfg.smem);
   else if (k == "launches") *value = (double)c->launches;
   else if (k == "sms") *value = c->sms;
-  else if (k == "regs_propagate") *value = c->lean ? pair_move_regs(c->lean_vk, c->lean_occ) : propagate_regs(c->ksel, false);
+  else if (k == "regs_propagate") *value = c->lean ? pair_move_regs(c->lean_vk, c->lean_occ) : c->small ? small_move_regs(c->plan.N[0]) : propagate_regs(c->ksel, false);
   else if (k == "regs_eval") *value = eval_regs(c->ksel, false);
   else if (k == "n_pair_passes") *value = c->plan.n2b;
   else if (k == "time_kernels_on") { c->time_kernels = 1; *value = 1; }

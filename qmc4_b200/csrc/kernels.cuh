@@ -141,6 +141,13 @@ int pair_move_regs(int vk, int occ);
 cudaError_t launch_pair_move(int vk, int occ, const LaunchCfg &cfg, int grid, cudaStream_t st, const Plan &plan, const DmcParams &dmc,
                              const double *dev_tab, const StepArgs &a, double *e_old);
 
+// small systems (kernels_small.cu): several walkers per warp
+int small_segment_width(int n);
+int small_walkers_per_cta(int n);
+int small_move_occupancy(int n);
+int small_move_regs(int n);
+cudaError_t launch_small_move(int n, int grid, cudaStream_t st, const Plan &plan, const DmcParams &dmc, const StepArgs &a, double *e_old);
+
 // forward walking (kernels_fw.cu)
 size_t fw_record_group_bytes(const Plan &plan, int max_sf_bins);
 cudaError_t configure_kernels_fw(int max_smem_optin);

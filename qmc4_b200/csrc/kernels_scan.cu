@@ -34,9 +34,13 @@ scan_multi_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int W = ctl->n_cur + (DECIDE ? a.n_adjust : 0);     /* pipeline 2: migration removed the tail / appended the arrivals */
   const int nblk = (int)gridDim.x;
-  if (t == 0) s_bid = atomicAdd(ws.ticket, 1);              /* logical index in arrival order: predecessors are running */
-  __syncthreads();
-  const int bid = s_bid;
+  const bool solo = nblk == 1;                               /* small populations: one CTA, no inter-CTA protocol at all */
+  if (!solo)
+    {
+      if (t == 0) s_bid = atomicAdd(ws.ticket, 1);          /* logical index in arrival order: predecessors are running */
+      __syncthreads();
+    }
+  const int bid = solo ? 0 : s_bid;
   const unsigned long long step = ctl->step;
   const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
   const double eT = (DECIDE && dmc.branching_on) ? branch_shift(dmc, ctl->gsum[0], ctl->gsum[1]) : 0.0;
@@ -89,19 +93,17 @@ scan_multi_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const
       int s = 0;
       for (int w = 0; w < SCAN_T / 32; ++w) s += s_warp[w];
       if (lane == 0)
-        { /* publish the total of this range ... */
+        { /* publish the total of this range in ONE word (bit 31 = valid) ... */
           s_tot = s;
-          ws.total[bid] = s;
-          __threadfence();
-          atomicExch(ws.flag + bid, 1u);
+          if (!solo) atomicExch(ws.flag + bid, 0x80000000u | (unsigned)s);
         }
       /* ... and look back: the lanes wait for different predecessors */
       int prefix = 0;
       for (int i = lane; i < bid; i += 32)
         {
-          while (atomicAdd(ws.flag + i, 0u) == 0u) { }
-          __threadfence();
-          prefix += *((volatile int *)(ws.total + i));
+          unsigned v;
+          while (((v = atomicAdd(ws.flag + i, 0u)) & 0x80000000u) == 0u) { }
+          prefix += (int)(v & 0x7fffffffu);
         }
       prefix = warp_sum_i(prefix);
       if (lane == 0) s_prefix = prefix;
@@ -176,26 +178,42 @@ scan_multi_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const
           acc += s_warp[w] & ((1 << 30) - 1);
           drp |= s_warp[w] >> 30;
         }
-      ws.esum[bid] = e;
-      ws.nacc[bid] = acc;
       if (drp) ctl->overflow = 1;
-      __threadfence();
-      s_last = (atomicAdd(ws.done, 1) == nblk - 1) ? 1 : 0;
+      if (solo)
+        {
+          s_red[0] = e;
+          s_warp[0] = acc;
+          s_last = 1;
+        }
+      else
+        {
+          ws.esum[bid] = e;
+          ws.nacc[bid] = acc;
+          __threadfence();
+          s_last = (atomicAdd(ws.done, 1) == nblk - 1) ? 1 : 0;
+        }
     }
   __syncthreads();
   if (!s_last) return;
   // ---- the CTA that finished last: totals in index order, control block, workspace reset for the next launch
-  __threadfence();
+  if (!solo) __threadfence();
   if (t == 0)
     {
       int total = 0, acc = 0;
       double e = 0.0;
-      for (int i = 0; i < nblk; ++i)
+      if (solo)
         {
-          total += *((volatile int *)(ws.total + i));
-          e += *((volatile double *)(ws.esum + i));
-          acc += *((volatile int *)(ws.nacc + i));
+          total = s_tot;
+          e = s_red[0];
+          acc = s_warp[0];
         }
+      else
+        for (int i = 0; i < nblk; ++i)
+          {
+            total += (int)(*((volatile unsigned *)(ws.flag + i)) & 0x7fffffffu);
+            e += *((volatile double *)(ws.esum + i));
+            acc += *((volatile int *)(ws.nacc + i));
+          }
       if (total == 0 && W > 0)
         { /* always keep at least a walker (branching.cpp:29-32) */
           a.n_desc[0] = 1;
@@ -242,10 +260,14 @@ scan_multi_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const
           for (int r = 0; r < NSUM; ++r) ctl->gsum[r] = ctl->lsum[r];
           if (dmc.branching_on) ctl->eshift = branch_shift(dmc, e, (double)newW);
         }
-      *ws.ticket = 0;
-      *ws.done = 0;
+      if (!solo)
+        {
+          *ws.ticket = 0;
+          *ws.done = 0;
+        }
     }
-  for (int i = t; i < nblk; i += SCAN_T) ws.flag[i] = 0u;
+  if (!solo)
+    for (int i = t; i < nblk; i += SCAN_T) ws.flag[i] = 0u;
 }
 
 } // namespace

@@ -142,3 +142,59 @@ def test_pair_kernel_traced_step_vs_oracle_at_baseline_sizes(port, N, L):
     up = port.update(cfg, cfg["timeStep"], R, tr["xi"], tr["u_metropolis"])
     np.testing.assert_array_equal(up["accepted"], tr["accepted"])
     s.close()
+
+
+def _traced_small(cfg, R, small):
+    from qmc4_b200.system import System
+    os.environ["QMC4_SMALL"] = "1" if small else "0"
+    os.environ["QMC4_LEAN"] = "0"
+    try:
+        s = System.from_input(cfg)
+        assert s.info("small_kernel") == (1 if small else 0)
+        s.upload(R)
+        tr = s.step_traced()
+        Rn, En = s.download(with_energy=True)
+        b = s.block_results()
+        wpw = s.info("small_walkers_per_warp")
+        s.close()
+    finally:
+        os.environ.pop("QMC4_SMALL", None)
+        os.environ.pop("QMC4_LEAN", None)
+    return tr, Rn, En, b, wpw
+
+
+def _small_cases():
+    out = {}
+    for N in (10, 7, 3):
+        out["trap_N%d" % N] = (cases.trap(N, walkers=37), np.random.default_rng(N).normal(0, 0.7, size=(37, 3 * N)), {10: 2, 7: 4, 3: 8}[N])
+    out["pbc_gg_N16"] = (cases.pbc(16, 2.6, walkers=21), np.random.default_rng(5).uniform(-2.6, 2.6, size=(21, 48)), 2)
+    out["pbc_squareWellJastrow_N12"] = (cases.pbc(12, 5.0, jastrow=cases.JASTROWS["squareWell"], pot="squareWell", walkers=19),
+                                        np.random.default_rng(6).uniform(-2.5, 2.5, size=(19, 36)), 2)
+    pt = cases.pbc(9, 3.0, jastrow=cases.JASTROWS["poschTeller"], pot=None, walkers=26)
+    pt["potentials"] = [{"kind": "poschTeller2b", "sets": [0, 0], "R0": 0.8}, {"kind": "dipolar2b", "sets": [0, 0], "D": 0.3}]
+    pt["lBox"] = [5.0, 5.0, 5.0]
+    out["pbc_poschTeller_dipolar_N9"] = (pt, np.random.default_rng(7).uniform(-2.5, 2.5, size=(26, 27)), 2)
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_small_cases()))
+def test_small_system_kernel_agrees_with_the_general_kernels_and_the_oracle(port, name):
+    """several walkers per warp (kernels_small.cu) against one warp per walker on the same step — identical random numbers,
+    proposals and decisions, sums that differ by the order of additions — and against dmcDriver::update in the oracle"""
+    cfg, R, per_warp = _small_cases()[name]
+    tg, Rg, Eg, bg, _ = _traced_small(cfg, R, small=False)
+    ts, Rs, Es, bs, wpw = _traced_small(cfg, R, small=True)
+    assert wpw == per_warp
+    np.testing.assert_array_equal(ts["xi"], tg["xi"])
+    np.testing.assert_array_equal(ts["Rprop"], tg["Rprop"])
+    np.testing.assert_array_equal(ts["u_metropolis"], tg["u_metropolis"])
+    assert _rel(ts["logpsi"], tg["logpsi"]) < 1e-12 and _rel(ts["lap"], tg["lap"]) < 1e-12 and _rel(ts["V"], tg["V"]) < 1e-12
+    assert _rel(ts["Fprop"], tg["Fprop"]) < 1e-12 and _rel(ts["Eprop"], tg["Eprop"]) < 1e-11 and _rel(ts["q"], tg["q"]) < 1e-9
+    np.testing.assert_array_equal(ts["accepted"], tg["accepted"])
+    np.testing.assert_array_equal(ts["n_desc"], tg["n_desc"])
+    assert bs["n_moves"] == bg["n_moves"] == len(R) and bs["n_accepted"] == bg["n_accepted"]
+    ep = port.eval(cfg, ts["Rprop"])
+    for k, t in (("logpsi", "logpsi"), ("grad", "Fprop"), ("lap", "lap"), ("V", "V"), ("E", "Eprop")):
+        assert _rel(ts[t], ep[k]) < 1e-10, k
+    up = port.update(cfg, cfg["timeStep"], R, ts["xi"], ts["u_metropolis"])
+    np.testing.assert_array_equal(up["accepted"], ts["accepted"])
