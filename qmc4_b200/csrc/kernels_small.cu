@@ -6,9 +6,9 @@
 // (16 lanes for 9..16 particles, 8 for 5..8, 4 below: 2, 4 or 8 walkers per warp), lane i of the segment owns particle i:
 //   * proposal: R' = R + tau F + sqrt(tau) xi with exactly the Philox draws of the general kernels (counter = {slot, dof/4,
 //     step, rank}), so trajectories do not depend on which kernel ran (dmcMoves.cpp:12-30, vmcMoves.cpp:11-35);
-//   * evaluation: the lane meets the other N-1 particles of its walker through the segment's strip of shared memory and
-//     accumulates ITS OWN gradient — every ordered pair is visited, nothing is scattered, no barrier wider than the segment;
-//     the pair scalars (log psi, laplacian, V) are counted by the lane with the larger index
+//   * evaluation: cyclic pair schedule inside the segment (lane i meets particle i+k, k = 1..N/2, every unordered pair once);
+//     the partner's share of the gradient travels back with one segmented shuffle per component, nothing is scattered and
+//     no barrier is wider than the segment
 //     (jastrowWavefunctionTwoBody.h:124-164, jastrowWavefunctionOneBody.h:53-85, potential.cpp:21-32, potentialTwoBody.h:23-33);
 //   * reductions: segmented xor-shuffles (the width argument of shfl), Green ratio (dmcMoves.cpp:32-57), Metropolis
 //     (metropolis.cpp:5-29), commit or carry the parent through (dmcDriver.cpp:56-84).
@@ -37,16 +37,18 @@ __global__ void __launch_bounds__(SMALL_THREADS, 4)
 small_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams dmc, const StepArgs a, double *e_old)
 {
   constexpr int WPC = SMALL_THREADS / SW;                 /* walkers per CTA */
-  __shared__ double sR[WPC][3 * 16];
+  __shared__ double sR[WPC][3 * SW];
+  __shared__ double sZ[WPC][3 * SW];
   const int n = plan.N[0], dofs = plan.dofs;
-  const int lane = threadIdx.x & 31, i = lane % SW, ws = threadIdx.x / SW;
+  const int lane = threadIdx.x & 31, i = lane % SW, ws = threadIdx.x / SW, segbase = lane - i;
   const Ctl *ctl = a.ctl;
   const int j0 = a.count < 0 ? 0 : (a.first < 0 ? ctl->n_cur + a.first + 1 : a.first);
   const int j1 = a.count < 0 ? ctl->n_cur : j0 + a.count;
   const unsigned long long step = ctl->step;
   const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32) | ((uint32_t)dmc.rank << 24);
   const double Lx = plan.L[0], Ly = plan.L[1], Lz = plan.L[2], ix = plan.Linv[0], iy = plan.Linv[1], iz = plan.Linv[2];
-  double *R = sR[ws];
+  double *R = sR[ws], *Z = sZ[ws];
+  const int K = n >> 1;                                   /* cyclic offsets 1..K; offset n/2 is half-populated when n is even */
 
   /* the segments of a warp run the same number of turns (full-warp shuffles stay legal); a segment without a walker idles */
   for (int jb = j0 + blockIdx.x * WPC; jb < j1; jb += gridDim.x * WPC)
@@ -64,17 +66,31 @@ small_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ Dmc
 #pragma unroll
           for (int d = 0; d < 3; ++d)
             {
+              ro[d] = Rold[d * n + i];
+              fo[d] = Fold[d * n + i];
+            }
+        }
+      /* deviates: lane c of the segment draws Philox block c = coordinates 4c..4c+3 (3n <= 4 SW; the stream of the general kernels) */
+      if (live && i * 4 < dofs)
+        {
+          const u32x4 rnd = philox4x32_10({(uint32_t)j, (uint32_t)i, step_lo, step_hi}, dmc.seed_lo, dmc.seed_hi);
+          double z[4];
+          normal_pair(rnd.x, rnd.y, z[0], z[1]);
+          normal_pair(rnd.z, rnd.w, z[2], z[3]);
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            if (i * 4 + m < dofs) Z[i * 4 + m] = z[m];
+        }
+      __syncwarp();
+      if (act)
+        {
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            {
               const int k = d * n + i;
-              ro[d] = Rold[k];
-              fo[d] = Fold[k];
-              /* the deviate of coordinate k is word k % 4 of the Philox block k / 4 (same stream as the general kernels) */
-              const u32x4 rnd = philox4x32_10({(uint32_t)j, (uint32_t)(k >> 2), step_lo, step_hi}, dmc.seed_lo, dmc.seed_hi);
-              double z0, z1;
-              if ((k & 2) == 0) normal_pair(rnd.x, rnd.y, z0, z1);
-              else normal_pair(rnd.z, rnd.w, z0, z1);
-              const double z = (k & 1) ? z1 : z0;
+              const double z = Z[k];
               rn[d] = fma(dmc.sqrt_tau, z, fma(dmc.tau, fo[d], ro[d]));
-              R[d * 16 + i] = rn[d];
+              R[d * SW + i] = rn[d];
               if (a.trace.xi) a.trace.xi[(size_t)j * dofs + k] = z;
             }
         }
@@ -82,57 +98,58 @@ small_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ Dmc
       // ---- evaluation of the proposal
       double lp = 0, lap = 0, V = 0, gx = 0, gy = 0, gz = 0;
       if (act)
+        for (int t = 0; t < plan.n1b; ++t)
+          { /* jastrowOneBodyWavefunction (laplacian has no factor 2) + harmonicPotential; "distance from the origin" is min-imaged */
+            const OneBodyTerm &T = plan.t1[t];
+            const double dx = min_image(rn[0], Lx, ix), dy = min_image(rn[1], Ly, iy), dz = min_image(rn[2], Lz, iz);
+            const double r = sqrt(dx * dx + dy * dy + dz * dz);
+            if (T.J.kind != J_NONE)
+              {
+                double d0, d1, d2;
+                eval_radial(T.J, a.coef, r, d0, d1, d2);
+                lap += d2 + 2 * d1 / r;
+                lp += d0;
+                gx += dx / r * d1;
+                gy += dy / r * d1;
+                gz += dz / r * d1;
+              }
+            if (T.has_pot) V += T.half_omega2 * r * r;
+          }
+      /* pairs: cyclic schedule inside the segment, each unordered pair once: lane i meets particle i+k and hands the partner's
+         share of the gradient to it with one segmented shuffle (the lane that met ME at this offset is i-k) */
+      for (int k = 1; k <= K; ++k)
         {
-          for (int t = 0; t < plan.n1b; ++t)
-            { /* jastrowOneBodyWavefunction (laplacian has no factor 2) + harmonicPotential; "distance from the origin" is min-imaged */
-              const OneBodyTerm &T = plan.t1[t];
-              const double dx = min_image(rn[0], Lx, ix), dy = min_image(rn[1], Ly, iy), dz = min_image(rn[2], Lz, iz);
-              const double r = sqrt(dx * dx + dy * dy + dz * dz);
-              if (T.J.kind != J_NONE)
-                {
-                  double d0, d1, d2;
-                  eval_radial(T.J, a.coef, r, d0, d1, d2);
-                  lap += d2 + 2 * d1 / r;
-                  lp += d0;
-                  gx += dx / r * d1;
-                  gy += dy / r * d1;
-                  gz += dz / r * d1;
-                }
-              if (T.has_pot) V += T.half_omega2 * r * r;
-            }
-          for (int q = 0; q < n; ++q)
+          int q = i + k;
+          if (q >= n) q -= n;
+          int from = i - k;
+          if (from < 0) from += n;
+          const bool pa = act && !((2 * k == n) && (i >= K));
+          const int qq = pa ? q : 0;
+          const double dx = min_image(rn[0] - R[qq], Lx, ix);
+          const double dy = min_image(rn[1] - R[SW + qq], Ly, iy);
+          const double dz = min_image(rn[2] - R[2 * SW + qq], Lz, iz);
+          const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+          double gsum = 0;
+          if (pa)
             {
-              if (q == i) continue;
-              const double dx = min_image(rn[0] - R[q], Lx, ix);
-              const double dy = min_image(rn[1] - R[16 + q], Ly, iy);
-              const double dz = min_image(rn[2] - R[32 + q], Lz, iz);
-              const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-              const bool owner = q < i;          /* the pair's scalars are counted once */
               double r = 0;
               bool have_r = false;
               for (int p = 0; p < plan.n2b; ++p)
                 {
                   const PairPass &P = plan.p2[p];
-                  double gr = 0;
                   if (P.J.kind == J_GAUSSIAN)
                     { /* u = -a r^2, u'/r = -2a, u'' = -2a */
-                      gr = -2.0 * P.J.p[0];
-                      if (owner)
-                        {
-                          lp = fma(-P.J.p[0], r2, lp);
-                          lap += -12.0 * P.J.p[0];
-                        }
+                      gsum += -2.0 * P.J.p[0];
+                      lp = fma(-P.J.p[0], r2, lp);
+                      lap += -12.0 * P.J.p[0];
                     }
                   else if (P.J.kind == J_GAUSSGAUSS)
                     {
                       const double e = exp_gg(r2, P.J.p);
                       const double al = P.J.p[0], u0 = P.J.p[1];
-                      gr = -2.0 * u0 * al * e;
-                      if (owner)
-                        {
-                          lp = fma(u0, e, lp);
-                          lap += e * (8.0 * al * al * u0 * r2 - 12.0 * al * u0);
-                        }
+                      gsum += -2.0 * u0 * al * e;
+                      lp = fma(u0, e, lp);
+                      lap += e * (8.0 * al * al * u0 * r2 - 12.0 * al * u0);
                     }
                   else if (P.J.kind != J_NONE)
                     {
@@ -143,31 +160,31 @@ small_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ Dmc
                         }
                       double d0, d1, d2;
                       eval_radial(P.J, a.coef, r, d0, d1, d2);
-                      gr = d1 / r;
-                      if (owner)
-                        {
-                          lp += d0;
-                          lap += 2 * (d2 + 2 * gr);      /* jastrowWavefunctionTwoBody.h:150, D = 3 */
-                        }
+                      const double gr = d1 / r;
+                      gsum += gr;
+                      lp += d0;
+                      lap += 2 * (d2 + 2 * gr);      /* jastrowWavefunctionTwoBody.h:150, D = 3 */
                     }
-                  gx = fma(gr, dx, gx);
-                  gy = fma(gr, dy, gy);
-                  gz = fma(gr, dz, gz);
-                  if (owner)
+                  if (P.vkind == V_STEP) V += (r2 <= P.v_thr2) ? P.v_val : 0.0;
+                  else if (P.vkind != V_NONE)
                     {
-                      if (P.vkind == V_STEP) V += (r2 <= P.v_thr2) ? P.v_val : 0.0;
-                      else if (P.vkind != V_NONE)
+                      if (!have_r)
                         {
-                          if (!have_r)
-                            {
-                              r = sqrt(r2);
-                              have_r = true;
-                            }
-                          V += eval_pair_potential(P.vkind, P.v_val, r);
+                          r = sqrt(r2);
+                          have_r = true;
                         }
+                      V += eval_pair_potential(P.vkind, P.v_val, r);
                     }
                 }
             }
+          const double cx = gsum * dx, cy = gsum * dy, cz = gsum * dz;      /* 0 on idle lanes */
+          gx += cx;
+          gy += cy;
+          gz += cz;
+          const int fl = segbase + (act ? from : i);
+          gx -= shfl_d(cx, fl);
+          gy -= shfl_d(cy, fl);
+          gz -= shfl_d(cz, fl);
         }
       // ---- Green ratio and |grad|^2 on this lane's three coordinates, then the walker's sums over its segment
       double qv = 0, f2 = 0;

@@ -19,6 +19,7 @@ def _run(pipeline, cfg, R, steps):
     else:
         os.environ.pop("QMC4_PIPELINE", None)       # pipeline 2 is the default
     os.environ["QMC4_LEAN"] = "0"                   # the general kernels of both pipelines share every summation order
+    os.environ["QMC4_SMALL"] = "0"
     try:
         s = System.from_input(cfg)
         assert s.info("pipeline") == pipeline
@@ -31,6 +32,7 @@ def _run(pipeline, cfg, R, steps):
     finally:
         os.environ.pop("QMC4_PIPELINE", None)
         os.environ.pop("QMC4_LEAN", None)
+        os.environ.pop("QMC4_SMALL", None)
     return b, Rn, En, g
 
 
