@@ -137,7 +137,7 @@ struct qmc_ctx {
   // the fused pipeline of kernels.cu, which runs with genealogical records, forceEnergy and the traced step also carry.
   int pipeline = 2;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_scan = nullptr, ev_ar = nullptr, ev_mig = nullptr;
+  cudaEvent_t ev_scan = nullptr, ev_ar = nullptr, ev_mig = nullptr, ev_move = nullptr;
   bool ar_pending = false;
   int *flags = nullptr;             // [cap] accepted bit per walker (move kernel -> scan)
   double *h_sums = nullptr;         // pinned copy of Ctl::gsum after the last all-reduce: what the migration planner reads
@@ -760,6 +760,17 @@ int ensure_scratch(qmc_ctx *c, size_t bytes, size_t ibytes)
   return 0;
 }
 
+// SMs the compute kernels may fill.  With a communicator two SMs are left to the communication stream: a persistent move
+// kernel that owns every CTA slot makes the all-reduce, the pack/unpack kernels and NCCL's point-to-point kernels wait for
+// its END, and a collective that found a slot first displaces a move CTA whose whole share of walkers then starts late
+// (measured at 8 GPUs: move kernel +9 %, step +7 %).  QMC4_COMM_SMS overrides.
+int compute_sms(const qmc_ctx *c)
+{
+  int reserve = c->nranks > 1 ? 2 : 0;
+  if (const char *e = getenv("QMC4_COMM_SMS")) reserve = std::max(0, std::min(16, atoi(e)));
+  return std::max(1, c->sms - reserve);
+}
+
 int grid_for(qmc_ctx *c, int64_t nW)
 {
   // persistent-style grid: a multiple of the SM count (resident CTAs per SM bounded by shared memory)
@@ -774,7 +785,7 @@ int grid_for(qmc_ctx *c, int64_t nW)
       if (v >= 1 && v <= 8) per_sm = v;
     }
   int64_t want = (nW + c->cfg.groups_per_cta - 1) / c->cfg.groups_per_cta;
-  int64_t g = std::min<int64_t>(want, (int64_t)c->sms * per_sm);
+  int64_t g = std::min<int64_t>(want, (int64_t)compute_sms(c) * per_sm);
   return (int)std::max<int64_t>(g, 1);
 }
 
@@ -960,8 +971,12 @@ int one_step_v2(qmc_ctx *c, int accumulate, const TraceDev *tr)
           plan_migration(c, src, amt, n_send, n_recv);
           if (n_send > 0 || n_recv > 0)
             {
-              const size_t dofs = c->plan.dofs, wsz = 2 * dofs + 2;
-              CK(launch_pack_tail(c->comm_stream, a.in, c->parent, c->ctl, (int)dofs, n_send, c->slab_send));
+              /* the tail walkers travel after their move of this step and before its branching: the sender has advanced them,
+                 the receiver appends the moved state to its output population (nothing is moved twice, no extra launch) */
+              const size_t dofs = c->plan.dofs, wsz = 2 * dofs + 4;
+              CK(cudaEventRecord(c->ev_move, c->stream));
+              CK(cudaStreamWaitEvent(c->comm_stream, c->ev_move, 0));
+              CK(launch_pack_moved(c->comm_stream, a.out, c->e_old, c->flags, c->ctl, (int)dofs, n_send, c->slab_send));
               NK(g_nccl.GroupStart());
               size_t off = 0;
               for (int r = 0; r < c->nranks; ++r)
@@ -972,25 +987,9 @@ int one_step_v2(qmc_ctx *c, int accumulate, const TraceDev *tr)
                   }
               if (n_recv > 0) NK(g_nccl.Recv(c->slab_recv, (size_t)n_recv * wsz, NCCL_FLOAT64, src[c->rank], c->comm, c->comm_stream));
               NK(g_nccl.GroupEnd());
-              CK(launch_unpack_append(c->comm_stream, a.in, c->parent, c->ctl, (int)dofs, n_send, n_recv, c->slab_recv));
+              CK(launch_unpack_moved(c->comm_stream, a.out, c->e_old, c->flags, c->ctl, (int)dofs, n_send, n_recv, c->slab_recv));
               CK(cudaEventRecord(c->ev_mig, c->comm_stream));
               CK(cudaStreamWaitEvent(c->stream, c->ev_mig, 0));
-              if (n_recv > 0)
-                { /* late arrivals are advanced within the same step (ptools.cpp:379-394, dmcDriver.cpp:133-136) */
-                  StepArgs t = a;
-                  t.first = -1 - n_send;       /* appended behind the walkers that stay */
-                  t.count = n_recv;
-                  const LaunchCfg &K = c->lean ? c->lean_cfg : c->cfg;
-                  const int g = std::max(1, std::min(K.grid, (n_recv + K.groups_per_cta - 1) / K.groups_per_cta));
-                  if (c->lean) CK(launch_pair_move(c->lean_vk, c->lean_occ, K, g, c->stream, c->plan, c->dmc, c->lean_tab, t, c->e_old));
-                  else if (c->small)
-                    {
-                      const int wpc = small_walkers_per_cta(c->plan.N[0]);
-                      CK(launch_small_move(c->plan.N[0], std::max(1, std::min(c->small_grid, (n_recv + wpc - 1) / wpc)), c->stream, c->plan, c->dmc, t, c->e_old));
-                    }
-                  else CK(launch_propagate_v2(c->ksel, c->cfg, g, c->stream, c->plan, c->dmc, t, c->e_old));
-                  c->launches += 1;
-                }
               a.n_adjust = n_recv - n_send;
               c->launches += (n_send > 0) + (n_recv > 0);
               c->mig_events += 1;
@@ -1219,6 +1218,7 @@ int qmc_create(qmc_ctx **out, int device, const double lBox[3], int nSpecies, co
     cudaEventCreateWithFlags(&c->ev_scan, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_ar, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_mig, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_move, cudaEventDisableTiming);
     if ((e = cudaHostAlloc((void **)&c->h_sums, sizeof(double) * NSUM, cudaHostAllocDefault)) != cudaSuccess) return bail(cudaGetErrorString(e));
     memset(c->h_sums, 0, sizeof(double) * NSUM);
   }
@@ -1274,6 +1274,7 @@ void qmc_destroy(qmc_ctx *c)
   if (c->ev_scan) cudaEventDestroy(c->ev_scan);
   if (c->ev_ar) cudaEventDestroy(c->ev_ar);
   if (c->ev_mig) cudaEventDestroy(c->ev_mig);
+  if (c->ev_move) cudaEventDestroy(c->ev_move);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   for (int b = 0; b < 2; ++b)
     {
@@ -1513,7 +1514,7 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
     { /* migration slabs sized once for a quarter of the capacity: no cudaMalloc/cudaFree (device-wide
          synchronisation) between the ranks' NCCL calls of qmc_rebalance in the common case */
       c->slab_walkers = (int)(capacity / 4 + 1);
-      c->slab_bytes = (size_t)c->slab_walkers * (2 * dofs + 2) * 8;
+      c->slab_bytes = (size_t)c->slab_walkers * (2 * dofs + 4) * 8;
       CK(cudaMalloc(&c->slab_send, c->slab_bytes));
       CK(cudaMalloc(&c->slab_recv, c->slab_bytes));
     }
@@ -1562,7 +1563,7 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
                 if (v >= 1 && v <= 8) per_sm = v;
               }
             const int64_t want = (capacity + L.groups_per_cta - 1) / L.groups_per_cta;
-            L.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sms * per_sm));
+            L.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)compute_sms(c) * per_sm));
             double tab[256];
             pair_exp_table(tab);
             CK(cudaMalloc(&c->lean_tab, sizeof tab));
@@ -1580,7 +1581,7 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
       {
         const int wpc = small_walkers_per_cta(P.N[0]);
         const int64_t want = (capacity + wpc - 1) / wpc;
-        c->small_grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sms * small_move_occupancy(P.N[0])));
+        c->small_grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)compute_sms(c) * small_move_occupancy(P.N[0])));
       }
   }
   c->n_partials = c->cfg.grid * c->cfg.groups_per_cta;
@@ -1628,7 +1629,7 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
             }
           const int per_sm = std::max(1, std::min(estimator_occupancy(c->est_occ, c->cfg.smem), c->est_occ));
           const int64_t want = (capacity + c->cfg.groups_per_cta - 1) / c->cfg.groups_per_cta;
-          c->est_grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->sms * per_sm));
+          c->est_grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)compute_sms(c) * per_sm));
           c->plan.hist_replicas = std::max(c->cfg.grid, c->est_grid);
         }
       CK(cudaMalloc(&c->hist, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8));

@@ -124,6 +124,10 @@ cudaError_t launch_scan_v2(cudaStream_t st, const DmcParams &dmc, const StepArgs
 cudaError_t launch_pack_tail(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, int dofs, int n_send, double *slab);
 cudaError_t launch_unpack_append(cudaStream_t st, const WalkerBuf &buf, int *parent, const Ctl *ctl, int dofs, int n_send, int n_recv,
                                  const double *slab);
+cudaError_t launch_pack_moved(cudaStream_t st, const WalkerBuf &out, const double *e_old, const int *flags, const Ctl *ctl, int dofs, int n_send,
+                              double *slab);
+cudaError_t launch_unpack_moved(cudaStream_t st, const WalkerBuf &out, double *e_old, int *flags, const Ctl *ctl, int dofs, int n_send, int n_recv,
+                                const double *slab);
 cudaError_t launch_population_checksum(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, unsigned long long *out);
 cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan &plan, const WalkerBuf &buf, const int *parent,
                               const Ctl *ctl, double *hist, int occ, int grid);

@@ -219,6 +219,54 @@ __global__ void unpack_append_kernel(WalkerBuf buf, int *parent, const Ctl *ctl,
         }
     }
 }
+// In-step migration (qmc_step): the tail walkers travel AFTER their move of step k and BEFORE its branching — the sender has
+// already advanced them, the receiver appends the moved state to its own output population and its scan branches them.
+// Nothing is moved twice and no second launch of the move kernel is needed for the arrivals (walkers in flight "skip
+// nothing", dmcDriver.cpp:133-136).  Slab record = {R'[dofs], F'[dofs], log psi', E', E of the parent, accepted}.
+__global__ void pack_moved_kernel(WalkerBuf out, const double *e_old, const int *flags, const Ctl *ctl, int dofs, int n_send, double *slab)
+{
+  const int first = ctl->n_cur - n_send;
+  for (int w = blockIdx.x; w < n_send; w += gridDim.x)
+    {
+      double *dst = slab + (size_t)w * (2 * dofs + 4);
+      const int j = first + w;
+      const size_t s = (size_t)j * dofs;
+      for (int k = threadIdx.x; k < dofs; k += blockDim.x)
+        {
+          dst[k] = out.R[s + k];
+          dst[dofs + k] = out.F[s + k];
+        }
+      if (threadIdx.x == 0)
+        {
+          dst[2 * dofs] = out.logpsi[j];
+          dst[2 * dofs + 1] = out.E[j];
+          dst[2 * dofs + 2] = e_old[j];
+          dst[2 * dofs + 3] = (double)flags[j];
+        }
+    }
+}
+__global__ void unpack_moved_kernel(WalkerBuf out, double *e_old, int *flags, const Ctl *ctl, int dofs, int n_send, int n_recv, const double *slab)
+{
+  const int idx0 = ctl->n_cur - n_send;          /* behind the walkers that stay */
+  for (int w = blockIdx.x; w < n_recv; w += gridDim.x)
+    {
+      const double *src = slab + (size_t)w * (2 * dofs + 4);
+      const int j = idx0 + w;
+      const size_t s = (size_t)j * dofs;
+      for (int k = threadIdx.x; k < dofs; k += blockDim.x)
+        {
+          out.R[s + k] = src[k];
+          out.F[s + k] = src[dofs + k];
+        }
+      if (threadIdx.x == 0)
+        {
+          out.logpsi[j] = src[2 * dofs];
+          out.E[j] = src[2 * dofs + 1];
+          e_old[j] = src[2 * dofs + 2];
+          flags[j] = (int)src[2 * dofs + 3];
+        }
+    }
+}
 // order-independent fingerprint of the current population (conservation checks of the migration): sum over the walkers of the
 // 64-bit patterns of (log psi, E) mixed by an odd multiplier, wrapping arithmetic
 __global__ void population_checksum_kernel(WalkerBuf buf, const int *parent, const Ctl *ctl, unsigned long long *out)
@@ -320,14 +368,28 @@ cudaError_t launch_estimators(const LaunchCfg &cfg, cudaStream_t st, const Plan 
 cudaError_t launch_pack_tail(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, int dofs, int n_send, double *slab)
 {
   if (n_send <= 0) return cudaSuccess;
-  QMC_LAUNCH(pack_tail_kernel, n_send < 512 ? n_send : 512, 128, 0, st, buf, parent, ctl, dofs, n_send, slab);
+  QMC_LAUNCH(pack_tail_kernel, n_send < 16 ? n_send : 16, 256, 0, st, buf, parent, ctl, dofs, n_send, slab);      /* fits the SMs left to the comm stream */
   return cudaGetLastError();
 }
 cudaError_t launch_unpack_append(cudaStream_t st, const WalkerBuf &buf, int *parent, const Ctl *ctl, int dofs, int n_send, int n_recv,
                                  const double *slab)
 {
   if (n_recv <= 0) return cudaSuccess;
-  QMC_LAUNCH(unpack_append_kernel, n_recv < 512 ? n_recv : 512, 128, 0, st, buf, parent, ctl, dofs, n_send, n_recv, slab);
+  QMC_LAUNCH(unpack_append_kernel, n_recv < 16 ? n_recv : 16, 256, 0, st, buf, parent, ctl, dofs, n_send, n_recv, slab);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_moved(cudaStream_t st, const WalkerBuf &out, const double *e_old, const int *flags, const Ctl *ctl, int dofs, int n_send,
+                              double *slab)
+{
+  if (n_send <= 0) return cudaSuccess;
+  QMC_LAUNCH(pack_moved_kernel, n_send < 16 ? n_send : 16, 256, 0, st, out, e_old, flags, ctl, dofs, n_send, slab);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack_moved(cudaStream_t st, const WalkerBuf &out, double *e_old, int *flags, const Ctl *ctl, int dofs, int n_send, int n_recv,
+                                const double *slab)
+{
+  if (n_recv <= 0) return cudaSuccess;
+  QMC_LAUNCH(unpack_moved_kernel, n_recv < 16 ? n_recv : 16, 256, 0, st, out, e_old, flags, ctl, dofs, n_send, n_recv, slab);
   return cudaGetLastError();
 }
 cudaError_t launch_population_checksum(cudaStream_t st, const WalkerBuf &buf, const int *parent, const Ctl *ctl, unsigned long long *out)
