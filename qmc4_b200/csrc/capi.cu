@@ -1525,6 +1525,9 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
       CK(cudaMemset(c->flags, 0, capacity * 4));
     }
   CK(cudaMalloc(&c->d_checksum, 8));
+  /* staging for qmc_download_walkers sized once for the whole capacity: growing it with the population meant a cudaFree +
+     cudaMalloc of hundreds of MB inside the end-to-end path (measured: up to 190 ms per call) */
+  if (ensure_scratch(c, (size_t)capacity * (dofs + 1) * 8, 0)) return 1;
   {
     const int nb = scan_max_blocks();
     CK(cudaMalloc(&c->scan_ws_i, (size_t)(2 + 3 * nb) * sizeof(int)));
