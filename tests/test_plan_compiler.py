@@ -113,13 +113,19 @@ def test_potential_or_estimator_without_a_wavefunction_on_the_same_sets_gets_its
 
 def test_three_body_plan():
     s = plan(cases.three_body(32, hs=0.4))
-    assert s.info("n_triplet_passes") == 1 and s.info("warps_per_walker") == 8
+    # undistinguishable triplets on <= 32 particles: the cyclic schedule (every triplet once), two warps per walker
+    assert s.info("n_triplet_passes") == 1 and s.info("triplet_cyclic") == 1 and s.info("warps_per_walker") == 2
     assert (s.info("triplet0.jkind"), s.info("triplet0.has_pot"), s.info("triplet0.hist"), s.info("triplet0.has_constraint")) == (J_GAUSSGAUSS, 1, 0, 1)
     assert s.info("triplet0.v_val") == -1.0                                # squareWell functor: -V0
     N = 32
     assert s.info("est0.norm") == pytest.approx(1 / ((2.5 / 50) * 4 * math.pi * N ** 3), rel=1e-15)     # trimerCorrelation.cpp:128-143
-    pair_table = 2 * (N * (N - 1) // 2)
-    assert s.info("smem_bytes") == 8 * (96 * 9 + 40 + pair_table) + 50 * 8
+    tables = 1024 * (1 + 2)                 # r2[32][32] + one pair-weight table per warp
+    groups = 4                              # walkers per 256-thread CTA
+    assert s.info("smem_bytes") == groups * 8 * (96 * 3 + 16 + tables) + 50 * 8
+    s.close()
+    # the three-visit pass remains for larger sets
+    s = plan(cases.three_body(40, L=5.5))
+    assert s.info("triplet_cyclic") == 0 and s.info("warps_per_walker") == 8
     s.close()
 
 
