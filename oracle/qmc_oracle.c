@@ -889,8 +889,11 @@ int orc_vmc_step_model(const orc_model *m, double sigma, int nW, const double *R
 
 /* ---- estimators --------------------------------------------------------------------------------- */
 static void hist_accumulate(double *sums, double minx, double dxinv, double a, double x)
-{ /* histogramAccumulator::accumulate (accumulators.h:117) */
+{ /* histogramAccumulator::accumulate (accumulators.h:117).  The reference has no lower bound: for x < minx - dx it
+   * writes before the array (undefined behaviour); such samples are dropped here and by the CUDA kernels.  minx - dx < x <
+   * minx truncates to bin 0 exactly as the reference's int conversion does. */
   int i = (int)((x - minx) * dxinv);
+  if (i < 0) return;
   sums[i] += a;
 }
 

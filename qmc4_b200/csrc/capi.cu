@@ -160,6 +160,8 @@ struct qmc_ctx {
   bool use_graphs = true;
   long graph_launches_per_replay = 0;
   long graph_replays = 0;
+  bool lean_hist = false;           // g(r) of the one-species shapes through pair_hist_kernel (kernels_pair.cu)
+  int lean_hist_grid = 0;
   bool small = false;               // kernels_small.cu: several walkers per warp (one species, N <= 16, no triplet terms)
   int small_grid = 0;
   bool trip_cyclic = false;
@@ -1018,7 +1020,8 @@ int one_step_v2(qmc_ctx *c, int accumulate, const TraceDev *tr)
   else if (T) CK(cudaEventRecord(T->a1, c->stream));
   if (accumulate && c->has_hist)
     {
-      CK(launch_estimators(c->cfg, c->stream, c->plan, c->buf[c->cur], c->parent, c->ctl, c->hist, c->est_occ, c->est_grid));
+      if (c->lean_hist) CK(launch_pair_hist(c->lean_hist_grid, c->stream, c->plan, 0, c->buf[c->cur], c->parent, c->ctl, c->hist));
+      else CK(launch_estimators(c->cfg, c->stream, c->plan, c->buf[c->cur], c->parent, c->ctl, c->hist, c->est_occ, c->est_grid));
       c->launches += 1;
     }
   if (T)
@@ -1635,6 +1638,18 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
           c->est_grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)compute_sms(c) * per_sm));
           c->plan.hist_replicas = std::max(c->cfg.grid, c->est_grid);
         }
+      {
+        const Plan &P = c->plan;
+        const char *he = getenv("QMC4_LEAN_HIST");
+        c->lean_hist = c->pipeline == 2 && c->lean && !(he && atoi(he) == 0) && P.nest == 1 && P.est[0].kind == QMC_EST_PAIRCORRELATION &&
+                       P.est[0].setA == 0 && P.est[0].setB == 0 && (int)pair_hist_smem(P) <= c->max_smem;
+        if (c->lean_hist)
+          {
+            const int64_t want = (capacity + 7) / 8;
+            c->lean_hist_grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)compute_sms(c) * std::min(4, pair_hist_occupancy(P))));
+            c->plan.hist_replicas = std::max(c->plan.hist_replicas, c->lean_hist_grid);
+          }
+      }
       CK(cudaMalloc(&c->hist, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8));
       CK(cudaMemset(c->hist, 0, (size_t)c->plan.hist_replicas * c->plan.hist_stride * 8));
       CK(cudaMalloc(&c->hist_out, (size_t)c->plan.hist_stride * 8));
@@ -2550,6 +2565,7 @@ int qmc_get_info(qmc_ctx *c, const char *key, double *value)
   else if (k == "pair_kernel") *value = c->lean ? 1 : 0;
   else if (k == "graph_replays") *value = (double)c->graph_replays;
   else if (k == "small_kernel") *value = c->small ? 1 : 0;
+  else if (k == "pair_hist_kernel") *value = c->lean_hist ? 1 : 0;
   else if (k == "small_walkers_per_warp") *value = c->small ? 32 / small_segment_width(c->plan.N[0]) : 0;
   else if (k == "triplet_cyclic") *value = c->trip_cyclic ? 1 : 0;
   else if (k == "triplet_table_entries") *value = c->plan.trip_count;

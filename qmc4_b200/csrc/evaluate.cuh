@@ -1343,6 +1343,26 @@ static __device__ QMC_NOINLINE void post_center_of_mass_squared(const Plan &plan
   G.sync();
 }
 
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 + 8 + 4 + 2 + 2 = 32 shuffles of 64 bits instead of 16 x 5: at every
+// stage a lane keeps half of its values and sends the other half to its partner.  On return lanes 2v and 2v+1 hold the total of
+// value v in v16[0].
+QMC_DEVICE void warp_reduce16(double (&v)[16], int lane)
+{
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1)
+    {
+      const bool up = (lane & bit) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i)
+        {
+          const double keep = up ? v[i + half] : v[i];
+          const double send = up ? v[i] : v[i + half];
+          v[i] = keep + shfl_xor_d(send, bit);
+        }
+    }
+  v[0] += shfl_xor_d(v[0], 1);
+}
+
 // Estimators that are evaluated on the FINAL configuration (in S.R) with its branching weight:
 // trimerCorrelationUnDis (trimerCorrelation.cpp:82-143) and the structure factor
 // (structureFactor.cpp:56-90 applied to coordinate 0; q_j = q0 + j*dq, structureFactor.cpp:23-40).
@@ -1489,16 +1509,18 @@ QMC_DEVICE void post_estimators(const Plan &plan, const Scratch &S, const Group 
                   pc[p] = c;
                   ps[p] = sn;
                 }
+              { /* 16 sums over the warp in one transposed reduction: lane 2v ends with value v (v < 8: re[v], else im[v-8]) */
+                double v16[16];
 #pragma unroll
-              for (int m = 0; m < CH; ++m)
-                {
-                  const double r = warp_sum(re[m]), q = warp_sum(im[m]);
-                  if (G.lane == 0 && j0 + m < bins)
-                    {
-                      auxw[2 * (j0 + m)] = r;
-                      auxw[2 * (j0 + m) + 1] = q;
-                    }
-                }
+                for (int m = 0; m < CH; ++m)
+                  {
+                    v16[m] = re[m];
+                    v16[CH + m] = im[m];
+                  }
+                warp_reduce16(v16, G.lane);
+                const int vi = G.lane >> 1, m = vi & 7;
+                if ((G.lane & 1) == 0 && j0 + m < bins) auxw[2 * (j0 + m) + (vi >> 3)] = v16[0];
+              }
             }
         }
       else

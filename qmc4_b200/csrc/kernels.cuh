@@ -145,6 +145,10 @@ int pair_move_regs(int vk, int occ);
 cudaError_t launch_pair_move(int vk, int occ, const LaunchCfg &cfg, int grid, cudaStream_t st, const Plan &plan, const DmcParams &dmc,
                              const double *dev_tab, const StepArgs &a, double *e_old);
 
+size_t pair_hist_smem(const Plan &plan);
+int pair_hist_occupancy(const Plan &plan);
+cudaError_t launch_pair_hist(int grid, cudaStream_t st, const Plan &plan, int e, const WalkerBuf &buf, const int *parent, const Ctl *ctl, double *hist);
+
 // small systems (kernels_small.cu): several walkers per warp
 int small_segment_width(int n);
 int small_walkers_per_cta(int n);

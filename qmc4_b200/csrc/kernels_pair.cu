@@ -566,6 +566,123 @@ template <int VK> const void *pair_variant(int v)
 }
 const void *pair_ptr(int vk, int v) { return vk == V_STEP ? pair_variant<V_STEP>(v) : pair_variant<V_NONE>(v); }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// g(r) of the one-species shapes over the post-branching population (pairCorrelation::accumulate, pairCorrelation.cpp:17-39,
+// over the population dmcDriver::accumulate iterates, dmcDriver.cpp:257-264: unit weight per walker).  Distances come from the
+// same fixed-point coordinates as the move kernel (wrapping integer subtraction, 3 FP64 per r^2 instead of 12 + 3 FRND), one warp
+// per walker, no gradients so no visitors and no shuffles, four pairs in flight per lane.  c/r^2 is quantised to 64-bit fixed point
+// and added to the CTA's shared-memory histogram with two native 32-bit atomics (hist_add_fixed), one flush per CTA per launch.
+struct HistParams {
+  double minx, maxx, dxinv;      // in box units (x / s) when the box is cubic, else in real units
+  double fxs;                    // fixed-point scale of 1/r2: a pair at r = maxx maps to 2^36
+  double flush;                  // (norm / s^2) / fxs : fixed-point total -> histogram sum
+  double direct;                 // norm / s^2         : weight of the exact fp64 path (contributions >= 2^40)
+  double s[3];                   // L_d 2^-64
+  int bins, offset, stride, cubic;
+};
+
+QMC_DEVICE void lean_hist_pair(const double r2, const bool ok, const HistParams &H, unsigned *fx, double *replica)
+{
+  const double y = rsqrt_fast(r2);
+  const double rr = r2 * y;
+  const int b = (int)((rr - H.minx) * H.dxinv);
+  const double t = y * y * H.fxs;
+  if (ok && rr < H.maxx && b >= 0)
+    {
+      const int bb = min(b, H.bins - 1);
+      if (t < HIST_FX_BYPASS) hist_add_fixed(fx + H.offset, H.stride, bb, (long long)t);
+      else atomicAdd(replica + H.offset + bb, H.direct * y * y);
+    }
+}
+
+template <bool CUBIC>
+__global__ void __launch_bounds__(CTA_THREADS, 4)
+pair_hist_kernel(const __grid_constant__ Plan plan, const __grid_constant__ HistParams H, const WalkerBuf buf, const int *parent, const Ctl *ctl,
+                 double *hist)
+{
+  QMC_DYNAMIC_SMEM(smem);
+  const int n = plan.N[0], dofs = plan.dofs;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned *fx = reinterpret_cast<unsigned *>(smem);                                  /* lo[stride], hi[stride] */
+  long long *X = reinterpret_cast<long long *>(smem + (size_t)2 * H.stride * sizeof(unsigned)) + (size_t)warp * dofs;
+  double *replica = hist + (size_t)blockIdx.x * H.stride;
+  for (int i = threadIdx.x; i < 2 * H.stride; i += CTA_THREADS) fx[i] = 0u;
+  __syncthreads();
+  const int nW = ctl->n_cur, nb = (n + 31) >> 5;
+  for (int j = blockIdx.x * (CTA_THREADS / 32) + warp; j < nW; j += gridDim.x * (CTA_THREADS / 32))
+    {
+      const double *R = buf.R + (size_t)parent[j] * dofs;
+      __syncwarp();
+      for (int k = lane; k < dofs; k += 32) X[k] = to_box_fraction(R[k], plan.Linv[k / n]);
+      __syncwarp();
+      for (int b = 0; b < nb; ++b)
+        {
+          const int ri = b * 32 + lane;
+          const bool rok = ri < n;
+          const long long xi = rok ? X[ri] : 0, yi = rok ? X[n + ri] : 0, zi = rok ? X[2 * n + ri] : 0;
+          /* full column blocks c < b: 32 columns each, lane l meets column (l + k) & 31 */
+          for (int c = 0; c < b; ++c)
+            {
+              const long long *xc = X + c * 32, *yc = xc + n, *zc = yc + n;
+#pragma unroll 4
+              for (int k = 0; k < 32; ++k)
+                {
+                  const int q = (lane + k) & 31;
+                  double dx = fx_diff(xi, xc[q]), dy = fx_diff(yi, yc[q]), dz = fx_diff(zi, zc[q]);
+                  if (!CUBIC)
+                    {
+                      dx *= H.s[0];
+                      dy *= H.s[1];
+                      dz *= H.s[2];
+                    }
+                  lean_hist_pair(fma(dz, dz, fma(dy, dy, dx * dx)), rok, H, fx, replica);
+                }
+            }
+          /* the block with itself: cyclic offsets 1..nc/2 (offset nc/2 half-populated when nc is even) */
+          {
+            const int nc = min(32, n - b * 32), K = nc >> 1;
+            const long long *xc = X + b * 32, *yc = xc + n, *zc = yc + n;
+#pragma unroll 4
+            for (int k = 1; k <= K; ++k)
+              {
+                int q = lane + k;
+                if (q >= nc) q -= nc;
+                const bool ok = rok && !((2 * k == nc) && (lane >= K));
+                const int qq = ok ? q : 0;
+                double dx = fx_diff(xi, xc[qq]), dy = fx_diff(yi, yc[qq]), dz = fx_diff(zi, zc[qq]);
+                if (!CUBIC)
+                  {
+                    dx *= H.s[0];
+                    dy *= H.s[1];
+                    dz *= H.s[2];
+                  }
+                double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                r2 = ok ? r2 : 1.0;              /* idle lanes: keep rsqrt away from 0 */
+                lean_hist_pair(r2, ok, H, fx, replica);
+              }
+          }
+        }
+    }
+  __syncthreads();
+  for (int b = threadIdx.x; b < H.bins; b += CTA_THREADS)
+    {
+      const unsigned lo = fx[H.offset + b], hi = fx[H.stride + H.offset + b];
+      const long long t = (long long)(((unsigned long long)hi << 32) | (unsigned long long)lo);
+      if (t != 0) atomicAdd(replica + H.offset + b, (double)t * H.flush);
+    }
+}
+
+#ifdef QMC_EMULATE
+template <bool CUBIC> void hist_tramp(void **p)
+{
+  pair_hist_kernel<CUBIC>(*(Plan *)p[0], *(HistParams *)p[1], *(WalkerBuf *)p[2], *(const int **)p[3], *(const Ctl **)p[4], *(double **)p[5]);
+}
+template <bool CUBIC> const void *hist_fn() { return (const void *)&hist_tramp<CUBIC>; }
+#else
+template <bool CUBIC> const void *hist_fn() { return (const void *)pair_hist_kernel<CUBIC>; }
+#endif
+
 } // namespace
 
 // warps per walker group of the tournament schedule: one warp per pair of 64-blocks of a round, a power of two <= 8
@@ -591,8 +708,47 @@ void pair_exp_table(double *tab256)
   for (int j = 0; j < 256; ++j) tab256[j] = (double)exp2l((long double)j / 256.0L);
 }
 
+
+size_t pair_hist_smem(const Plan &plan) { return (size_t)2 * plan.hist_stride * sizeof(unsigned) + (size_t)(CTA_THREADS / 32) * plan.dofs * sizeof(long long); }
+
+int pair_hist_occupancy(const Plan &plan)
+{
+  const bool cubic = plan.L[0] == plan.L[1] && plan.L[1] == plan.L[2];
+  int nblk = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, cubic ? hist_fn<true>() : hist_fn<false>(), CTA_THREADS, pair_hist_smem(plan)) != cudaSuccess) return 1;
+  return nblk < 1 ? 1 : nblk;
+}
+
+// the pairCorrelation estimator `e` of the plan through the fixed-point kernel (hist = the replicas [grid][hist_stride])
+cudaError_t launch_pair_hist(int grid, cudaStream_t st, const Plan &plan, int e, const WalkerBuf &buf, const int *parent, const Ctl *ctl, double *hist)
+{
+  const Estimator &E = plan.est[e];
+  const long double two64 = 18446744073709551616.0L;
+  HistParams H;
+  H.cubic = (plan.L[0] == plan.L[1] && plan.L[1] == plan.L[2]) ? 1 : 0;
+  for (int d = 0; d < 3; ++d) H.s[d] = (double)((long double)plan.L[d] / two64);
+  const long double s = H.cubic ? (long double)plan.L[0] / two64 : 1.0L;      /* length unit of the pair loop */
+  H.minx = (double)((long double)E.minx / s);
+  H.maxx = (double)((long double)E.maxx / s);
+  H.dxinv = (double)((long double)E.dxinv * s);
+  H.fxs = (double)(68719476736.0L * ((long double)E.maxx / s) * ((long double)E.maxx / s));      /* 2^36 at r = maxx */
+  H.direct = (double)((long double)E.norm / (s * s));
+  H.flush = (double)((long double)E.norm / (s * s) / (long double)H.fxs);
+  H.bins = E.bins;
+  H.offset = E.offset;
+  H.stride = plan.hist_stride;
+  const WalkerBuf b = buf;
+  void *args[] = {(void *)&plan, (void *)&H, (void *)&b, (void *)&parent, (void *)&ctl, (void *)&hist};
+  return cudaLaunchKernel(H.cubic ? hist_fn<true>() : hist_fn<false>(), dim3(grid), dim3(CTA_THREADS), args, pair_hist_smem(plan), st);
+}
+
 cudaError_t configure_kernels_pair(int max_smem_optin)
 {
+  for (int cub = 0; cub < 2; ++cub)
+    {
+      cudaError_t e = cudaFuncSetAttribute(cub ? hist_fn<true>() : hist_fn<false>(), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+      if (e != cudaSuccess) return e;
+    }
   for (int vk : {(int)V_STEP, (int)V_NONE})
     for (int occ = 0; occ <= 2; ++occ)
       {

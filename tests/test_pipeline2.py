@@ -200,3 +200,42 @@ def test_small_system_kernel_agrees_with_the_general_kernels_and_the_oracle(port
         assert _rel(ts[t], ep[k]) < 1e-10, k
     up = port.update(cfg, cfg["timeStep"], R, ts["xi"], ts["u_metropolis"])
     np.testing.assert_array_equal(up["accepted"], ts["accepted"])
+
+
+def _hist_after_steps(cfg, R, lean_hist, steps=2):
+    from qmc4_b200.system import System
+    os.environ["QMC4_LEAN_HIST"] = "1" if lean_hist else "0"
+    try:
+        s = System.from_input(cfg)
+        assert s.info("pair_hist_kernel") == (1 if lean_hist else 0)
+        s.upload(R)
+        pops = []
+        for _ in range(steps):
+            s.step(1, 1)
+            pops.append(s.download())          # the post-branching population the estimator just accumulated over
+        sums, w = s.estimator(0)
+        s.close()
+    finally:
+        os.environ.pop("QMC4_LEAN_HIST", None)
+    return sums, w, pops
+
+
+@pytest.mark.parametrize("N,L,bins,minx", [(16, 2.6, 26, 0.0), (33, 3.2, 64, 0.1), (64, 4.0, 1000, 0.0), (100, 4.7, 200, 0.0)])
+def test_pair_hist_kernel_vs_general_estimator_and_oracle(port, N, L, bins, minx):
+    """g(r) through the fixed-point-coordinate kernel (kernels_pair.cu) == the general estimator kernel == the oracle's
+    pairCorrelation::accumulate over the post-branching populations with unit weight"""
+    W = 40
+    meas = [{"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": bins, "minx": minx, "maxx": L / 2}]
+    cfg = cases.pbc(N, L, walkers=W, meas=meas)
+    R = np.random.default_rng(3 * N).uniform(-L, L, size=(W, 3 * N))
+    sg, wg, pg = _hist_after_steps(cfg, R, lean_hist=False)
+    sl, wl, pl = _hist_after_steps(cfg, R, lean_hist=True)
+    assert wl == wg == sum(len(p) for p in pl)
+    for a, b in zip(pg, pl):
+        np.testing.assert_array_equal(a, b)            # same trajectory: the estimator kernels do not touch the walkers
+    assert _rel(sl, sg) < 1e-9
+    ref = np.zeros(bins)
+    for p in pl:
+        rs, rw = port.histogram(cfg, p, 0, bins)
+        ref += rs
+    assert _rel(sl, ref) < 1e-9
