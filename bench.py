@@ -245,7 +245,19 @@ def measure(s, cfg, cfgno, steps, warmup, dmc_steps, equil, flush, barrier, worl
     """Equilibrate, warm up, time `steps` bench steps of `dmc_steps` DMC steps each with CUDA events on the library's
     stream (qmc_step), max over ranks.  Returns the measurement dict of this rank (global quantities where stated)."""
     pairs, trip, flops_per_move, bytes_per_move = work_per_move(cfg)
-    s.step(equil, 1)
+    verbose = bool(os.environ.get("QMC4_BENCH_VERBOSE"))
+    if verbose:         # population of this rank along the equilibration (diagnostics on stderr)
+        done = 0
+        while done < equil:
+            n = min(10, equil - done)
+            s.step(n, 1)
+            done += n
+            b = s.block_results()
+            print("[bench rank %d] equil step %d: population %d, E/N %.6g, migrated out/in %d/%d" % (
+                rank, done, b["population"], b["energy_sum"] / max(b["energy_count"], 1) / sum(cfg["N"]),
+                s.info("migrated_out"), s.info("migrated_in")), file=sys.stderr, flush=True)
+    else:
+        s.step(equil, 1)
     s.block_results()
     for _ in range(warmup):
         if flush is not None:

@@ -1552,17 +1552,22 @@ int qmc_set_dmc(qmc_ctx *c, double timeStep, int64_t targetWalkers, int64_t delt
     if (c->lean)
       {
         c->lean_vk = P.p2[0].vkind;
-        if (const char *o = getenv("QMC4_LEAN_VARIANT")) c->lean_occ = std::max(0, std::min(2, atoi(o)));
+        if (const char *o = getenv("QMC4_LEAN_VARIANT")) c->lean_occ = std::max(0, std::min(3, atoi(o)));
         LaunchCfg &L = c->lean_cfg;
-        L.block = pair_variant_threads(c->lean_occ);
-        L.nwarps_per_group = std::min(pair_warps_per_walker(P.N[0]), L.block / 32);
-        L.groups_per_cta = (L.block / 32) / L.nwarps_per_group;
-        L.smem = pair_group_bytes(P, L.nwarps_per_group) * L.groups_per_cta + pair_cta_extra_bytes();
+        for (;;)
+          {
+            L.block = pair_variant_threads(c->lean_occ);
+            L.nwarps_per_group = std::min(pair_warps_per_walker(P.N[0]), L.block / 32);
+            L.groups_per_cta = (L.block / 32) / L.nwarps_per_group;
+            L.smem = pair_group_bytes(P, L.nwarps_per_group) * L.groups_per_cta + pair_cta_extra_bytes(c->lean_occ);
+            if ((int)L.smem <= c->max_smem || c->lean_occ != 3) break;
+            c->lean_occ = 0;      /* 16 walker groups + the replicated table do not fit: two 256-thread CTAs with one table each */
+          }
         if ((int)L.smem > c->max_smem) c->lean = false;
         else
           {
             int per_sm = std::max(1, std::min(pair_move_occupancy(c->lean_vk, c->lean_occ, L.smem), 2048 / L.block));
-            per_sm = std::min(per_sm, c->lean_occ == 2 ? 5 : c->lean_occ == 1 ? 4 : 2);
+            per_sm = std::min(per_sm, c->lean_occ == 3 ? 1 : c->lean_occ == 2 ? 5 : c->lean_occ == 1 ? 4 : 2);
             if (const char *e2 = getenv("QMC4_CTAS_PER_SM"))
               {
                 const int v = atoi(e2);

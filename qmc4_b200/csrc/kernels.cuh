@@ -136,7 +136,7 @@ int estimator_occupancy(int occ, size_t smem);
 // the hot kernel of the one-species / one-pair-pass shapes (kernels_pair.cu): move step with the tournament tile schedule
 int pair_warps_per_walker(int n);
 size_t pair_group_bytes(const Plan &plan, int nwarps);
-size_t pair_cta_extra_bytes();
+size_t pair_cta_extra_bytes(int variant);
 int pair_variant_threads(int variant);
 void pair_exp_table(double *tab256);
 cudaError_t configure_kernels_pair(int max_smem_optin);

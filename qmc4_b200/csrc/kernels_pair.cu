@@ -66,6 +66,10 @@ QMC_DEVICE double fx_diff(const long long a, const long long b)
   return __ll2double_rn((long long)((unsigned long long)a - (unsigned long long)b));   /* wrapping subtraction = minimum image */
 }
 
+// TS: table stride in doubles.  TS = 1: one copy, every lane gathers from the same 2 KB (random bank conflicts, 3.6 excess wavefronts per
+// lookup measured); TS = 16: 16 interleaved copies, `tab` already points at the lane's own copy (lane & 15), so the 16 lanes of a half-warp
+// hit 16 different 8-byte bank pairs whatever their indices: conflict-free by construction.
+template <int TS>
 QMC_DEVICE double exp_tab(const double r2, const LeanParams &E, const double *tab)
 {
   const double MAGIC = 6755399441055744.0;      // 2^52 + 2^51
@@ -78,7 +82,7 @@ QMC_DEVICE double exp_tab(const double r2, const LeanParams &E, const double *ta
   q = fma(q, f, E.c1);
   q = fma(q, f, 1.0);
   n = max(n, -256000);                          /* exp(-693) ~ 1e-301: zero to every accumulator it can meet */
-  const double e = tab[n & 255] * q;
+  const double e = tab[(n & 255) * TS] * q;
   const int hi = __double2hiint(e) + ((n >> 8) << 20);
   return __hiloint2double(hi, __double2loint(e));
 }
@@ -97,7 +101,7 @@ constexpr int PAIR_UNROLL = QMC_PAIR_UNROLL;
 // One tile: rows = block rb (lane l owns row particle rb*32+l), columns = block cb.  DIAG: rb == cb, cyclic offsets 1..16
 // (offset 16 half-populated).  MASKED: the row and/or column block is the ragged last block of the species.
 // Two independent pairs per lane and step: stream 0 meets column (l + OFF0 + k), stream 1 column (l + OFF1 + k).
-template <int VK, bool CUBIC, bool DIAG, bool MASKED>
+template <int VK, bool CUBIC, bool DIAG, bool MASKED, int TS>
 QMC_DEVICE void lean_tile(const LeanParams &LP, const double *tab, const long long *xs, const int n, const int rb,
                           const int cb, long long *T, const int lane, double *acc, LeanSums &S)
 {
@@ -146,8 +150,8 @@ QMC_DEVICE void lean_tile(const LeanParams &LP, const double *tab, const long lo
         }
       const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
       const double r21 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
-      double e0 = exp_tab(r20, LP, tab);
-      double e1 = exp_tab(r21, LP, tab);
+      double e0 = exp_tab<TS>(r20, LP, tab);
+      double e1 = exp_tab<TS>(r21, LP, tab);
       bool a0 = true, a1 = true;
       if (DIAG) a1 = !((k == IT - 1) && (lane >= 16));          /* offset 16: every pair appears in two lanes, keep one */
       if (MASKED)
@@ -220,7 +224,7 @@ QMC_DEVICE void lean_tile(const LeanParams &LP, const double *tab, const long lo
 // and meets column (l + k) mod 32 with BOTH, so one column load and one visitor rotation serve two pairs (3 LDS + 6 SHFL per
 // two pairs; lean_tile: 6 + 12).  The row gradients stay in registers over both column blocks of the 64-block m'.
 // Full blocks only (the caller falls back to lean_tile on ragged edges).
-template <int VK, bool CUBIC>
+template <int VK, bool CUBIC, int TS>
 QMC_DEVICE void lean_pairblock(const LeanParams &LP, const double *tab, const long long *xs, const int n, const int m, const int mp,
                                long long *T, const int lane, double *acc, LeanSums &S)
 {
@@ -264,8 +268,8 @@ QMC_DEVICE void lean_pairblock(const LeanParams &LP, const double *tab, const lo
             }
           const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
           const double r21 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
-          const double e0 = exp_tab(r20, LP, tab);
-          const double e1 = exp_tab(r21, LP, tab);
+          const double e0 = exp_tab<TS>(r20, LP, tab);
+          const double e1 = exp_tab<TS>(r21, LP, tab);
           S.s0 += e0;
           S.s1 = fma(e0, r20, S.s1);
           S.s0 += e1;
@@ -329,7 +333,7 @@ QMC_DEVICE LeanScratch make_lean_scratch(const Plan &plan, unsigned char *smem, 
 // Schedule: the particles are cut in 64-blocks; the pairs of DIFFERENT 64-blocks are visited in the rounds of a round-robin
 // tournament (in one round every 64-block belongs to at most one warp, which therefore owns its gradient rows), then every
 // 64-block is paired with itself (two diagonal 32-tiles + one 32 x 32 tile).
-template <int VK, bool CUBIC>
+template <int VK, bool CUBIC, int TS>
 QMC_DEVICE EvalResult lean_evaluate(const Plan &plan, const LeanParams &LP, const double *tab, const LeanScratch &S, const Group &G)
 {
   const int n = plan.N[0], dofs = plan.dofs;
@@ -364,14 +368,14 @@ QMC_DEVICE EvalResult lean_evaluate(const Plan &plan, const LeanParams &LP, cons
             }
           if (a >= nB || b >= nB) continue;        /* bye */
           const int M = a > b ? a : b, Mp = a > b ? b : a;
-          if (M * 64 + 64 <= n) lean_pairblock<VK, CUBIC>(LP, tab, S.X, n, M, Mp, S.strip, G.lane, S.acc, sums);
+          if (M * 64 + 64 <= n) lean_pairblock<VK, CUBIC, TS>(LP, tab, S.X, n, M, Mp, S.strip, G.lane, S.acc, sums);
           else
             { /* ragged last 64-block: its one or two 32-blocks against the two (full) 32-blocks of Mp */
               for (int rb = 2 * M; rb < nb; ++rb)
                 for (int cb = 2 * Mp; cb < 2 * Mp + 2; ++cb)
                   {
-                    if (rb * 32 + 32 <= n) lean_tile<VK, CUBIC, false, false>(LP, tab, S.X, n, rb, cb, S.strip, G.lane, S.acc, sums);
-                    else lean_tile<VK, CUBIC, false, true>(LP, tab, S.X, n, rb, cb, S.strip, G.lane, S.acc, sums);
+                    if (rb * 32 + 32 <= n) lean_tile<VK, CUBIC, false, false, TS>(LP, tab, S.X, n, rb, cb, S.strip, G.lane, S.acc, sums);
+                    else lean_tile<VK, CUBIC, false, true, TS>(LP, tab, S.X, n, rb, cb, S.strip, G.lane, S.acc, sums);
                   }
             }
         }
@@ -380,19 +384,19 @@ QMC_DEVICE EvalResult lean_evaluate(const Plan &plan, const LeanParams &LP, cons
   for (int d = G.gwarp; d < nB; d += G.nwarps)
     {
       const int b0 = 2 * d, b1 = 2 * d + 1;
-      if (b0 * 32 + 32 <= n) lean_tile<VK, CUBIC, true, false>(LP, tab, S.X, n, b0, b0, S.strip, G.lane, S.acc, sums);
-      else lean_tile<VK, CUBIC, true, true>(LP, tab, S.X, n, b0, b0, S.strip, G.lane, S.acc, sums);
+      if (b0 * 32 + 32 <= n) lean_tile<VK, CUBIC, true, false, TS>(LP, tab, S.X, n, b0, b0, S.strip, G.lane, S.acc, sums);
+      else lean_tile<VK, CUBIC, true, true, TS>(LP, tab, S.X, n, b0, b0, S.strip, G.lane, S.acc, sums);
       if (b1 < nb)
         {
           if (b1 * 32 + 32 <= n)
             {
-              lean_tile<VK, CUBIC, true, false>(LP, tab, S.X, n, b1, b1, S.strip, G.lane, S.acc, sums);
-              lean_tile<VK, CUBIC, false, false>(LP, tab, S.X, n, b1, b0, S.strip, G.lane, S.acc, sums);
+              lean_tile<VK, CUBIC, true, false, TS>(LP, tab, S.X, n, b1, b1, S.strip, G.lane, S.acc, sums);
+              lean_tile<VK, CUBIC, false, false, TS>(LP, tab, S.X, n, b1, b0, S.strip, G.lane, S.acc, sums);
             }
           else
             {
-              lean_tile<VK, CUBIC, true, true>(LP, tab, S.X, n, b1, b1, S.strip, G.lane, S.acc, sums);
-              lean_tile<VK, CUBIC, false, true>(LP, tab, S.X, n, b1, b0, S.strip, G.lane, S.acc, sums);
+              lean_tile<VK, CUBIC, true, true, TS>(LP, tab, S.X, n, b1, b1, S.strip, G.lane, S.acc, sums);
+              lean_tile<VK, CUBIC, false, true, TS>(LP, tab, S.X, n, b1, b0, S.strip, G.lane, S.acc, sums);
             }
         }
     }
@@ -425,7 +429,7 @@ QMC_DEVICE EvalResult lean_evaluate(const Plan &plan, const LeanParams &LP, cons
   return out;
 }
 
-template <int VK, int THREADS, int MINB>
+template <int VK, int THREADS, int MINB, int TS>
 __global__ void __launch_bounds__(THREADS, MINB)
 pair_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcParams dmc, const __grid_constant__ LeanParams LP, const StepArgs a,
                  double *e_old, int nwarps_per_group, size_t group_bytes)
@@ -434,10 +438,11 @@ pair_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
   const Group G = make_group(nwarps_per_group);
   const int groups = (THREADS / 32) / nwarps_per_group;
   const int g = (threadIdx.x >> 5) / nwarps_per_group;
-  double *tab = reinterpret_cast<double *>(smem);        /* 2^(j/256) at the start of the CTA's shared memory (fixed address) */
-  const LeanScratch S = make_lean_scratch(plan, smem + 256 * sizeof(double), g, nwarps_per_group, G.gwarp, group_bytes);
-  for (int i = threadIdx.x; i < 256; i += THREADS) tab[i] = LP.tab[i];
+  double *tab0 = reinterpret_cast<double *>(smem);       /* 2^(j/256), TS interleaved copies, at the start of the CTA's shared memory */
+  const LeanScratch S = make_lean_scratch(plan, smem + (size_t)256 * TS * sizeof(double), g, nwarps_per_group, G.gwarp, group_bytes);
+  for (int i = threadIdx.x; i < 256 * TS; i += THREADS) tab0[i] = LP.tab[i / TS];
   __syncthreads();
+  const double *tab = tab0 + (threadIdx.x & (TS - 1));   /* this lane's copy */
   const int dofs = plan.dofs;
   const Ctl *ctl = a.ctl;
   const int j0 = a.count < 0 ? 0 : (a.first < 0 ? ctl->n_cur + a.first + 1 : a.first);
@@ -469,7 +474,7 @@ pair_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
             }
         }
       G.sync();
-      const EvalResult r = LP.cubic ? lean_evaluate<VK, true>(plan, LP, tab, S, G) : lean_evaluate<VK, false>(plan, LP, tab, S, G);
+      const EvalResult r = LP.cubic ? lean_evaluate<VK, true, TS>(plan, LP, tab, S, G) : lean_evaluate<VK, false, TS>(plan, LP, tab, S, G);
       // ---- log Green ratio and |grad|^2
       double q = 0, f2 = 0;
       for (int k = G.gtid; k < dofs; k += G.gsize)
@@ -549,20 +554,22 @@ pair_move_kernel(const __grid_constant__ Plan plan, const __grid_constant__ DmcP
 }
 
 #ifdef QMC_EMULATE   /* tests/emu: cudaLaunchKernel gets a trampoline that unpacks the argument array */
-template <int VK, int THREADS, int MINB> void pair_tramp(void **p)
+template <int VK, int THREADS, int MINB, int TS> void pair_tramp(void **p)
 {
-  pair_move_kernel<VK, THREADS, MINB>(*(Plan *)p[0], *(DmcParams *)p[1], *(LeanParams *)p[2], *(StepArgs *)p[3], *(double **)p[4], *(int *)p[5],
+  pair_move_kernel<VK, THREADS, MINB, TS>(*(Plan *)p[0], *(DmcParams *)p[1], *(LeanParams *)p[2], *(StepArgs *)p[3], *(double **)p[4], *(int *)p[5],
                                       *(size_t *)p[6]);
 }
-template <int VK, int THREADS, int MINB> const void *pair_fn() { return (const void *)&pair_tramp<VK, THREADS, MINB>; }
+template <int VK, int THREADS, int MINB, int TS> const void *pair_fn() { return (const void *)&pair_tramp<VK, THREADS, MINB, TS>; }
 #else
-template <int VK, int THREADS, int MINB> const void *pair_fn() { return (const void *)pair_move_kernel<VK, THREADS, MINB>; }
+template <int VK, int THREADS, int MINB, int TS> const void *pair_fn() { return (const void *)pair_move_kernel<VK, THREADS, MINB, TS>; }
 #endif
 
-// launch geometries compiled: variant 0 = 256 threads x 2 CTAs/SM (<= 128 registers), 1 = 128 x 4, 2 = 128 x 5 (<= 96 registers)
+// launch geometries compiled: variant 0 = 256 threads x 2 CTAs/SM (<= 128 registers), 1 = 128 x 4, 2 = 128 x 5 (<= 96 registers),
+// 3 = 512 x 1 with 16 interleaved copies of the exp table (32 KB, shared by the 4 walker groups of the SM's single CTA: two CTAs could not
+// afford it) -- the same 16 warps per SM as variant 0, conflict-free table gathers
 template <int VK> const void *pair_variant(int v)
 {
-  return v == 2 ? pair_fn<VK, 128, 5>() : v == 1 ? pair_fn<VK, 128, 4>() : pair_fn<VK, 256, 2>();
+  return v == 3 ? pair_fn<VK, 512, 1, 16>() : v == 2 ? pair_fn<VK, 128, 5, 1>() : v == 1 ? pair_fn<VK, 128, 4, 1>() : pair_fn<VK, 256, 2, 1>();
 }
 const void *pair_ptr(int vk, int v) { return vk == V_STEP ? pair_variant<V_STEP>(v) : pair_variant<V_NONE>(v); }
 
@@ -700,7 +707,7 @@ size_t pair_group_bytes(const Plan &plan, int nwarps)
   d = (d + 1) & ~(size_t)1;
   return d * 8;
 }
-size_t pair_cta_extra_bytes() { return 256 * sizeof(double); }     /* the exp table */
+size_t pair_cta_extra_bytes(int variant) { return (size_t)256 * sizeof(double) * (variant == 3 ? 16 : 1); }     /* the exp table(s) */
 
 // the 256 table values 2^(j/256) (host, correctly rounded from long double)
 void pair_exp_table(double *tab256)
@@ -750,7 +757,7 @@ cudaError_t configure_kernels_pair(int max_smem_optin)
       if (e != cudaSuccess) return e;
     }
   for (int vk : {(int)V_STEP, (int)V_NONE})
-    for (int occ = 0; occ <= 2; ++occ)
+    for (int occ = 0; occ <= 3; ++occ)
       {
         cudaError_t e = cudaFuncSetAttribute(pair_ptr(vk, occ), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
         if (e != cudaSuccess) return e;
@@ -758,7 +765,7 @@ cudaError_t configure_kernels_pair(int max_smem_optin)
   return cudaSuccess;
 }
 
-int pair_variant_threads(int v) { return v == 0 ? 256 : 128; }
+int pair_variant_threads(int v) { return v == 3 ? 512 : v == 0 ? 256 : 128; }
 
 int pair_move_occupancy(int vk, int occ, size_t smem)
 {
@@ -778,7 +785,7 @@ cudaError_t launch_pair_move(int vk, int occ, const LaunchCfg &cfg, int grid, cu
                              const double *dev_tab, const StepArgs &a, double *e_old)
 {
   int nw = cfg.nwarps_per_group;
-  size_t gb = (cfg.smem - pair_cta_extra_bytes()) / cfg.groups_per_cta;
+  size_t gb = (cfg.smem - pair_cta_extra_bytes(occ)) / cfg.groups_per_cta;
   /* constants of the pair loop, folded on the host (jastrowGaussGauss.h:19-21: u = u0 exp(-alpha r^2), alpha = 1/(2 r0^2)) */
   const PairPass &PP = plan.p2[0];
   const long double al = PP.J.p[0], ln2 = 0.693147180559945309417232121458176568L;

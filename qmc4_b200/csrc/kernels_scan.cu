@@ -267,7 +267,10 @@ scan_multi_kernel(const __grid_constant__ DmcParams dmc, const StepArgs a, const
         }
     }
   if (!solo)
-    for (int i = t; i < nblk; i += SCAN_T) ws.flag[i] = 0u;
+    {
+      __syncthreads();      /* thread 0 has summed the published totals: only now may the other threads clear them for the next launch */
+      for (int i = t; i < nblk; i += SCAN_T) ws.flag[i] = 0u;
+    }
 }
 
 } // namespace

@@ -24,7 +24,8 @@ FAST = "not statistical and not population_control and not determinism and not n
 SLOW = os.environ.get("QMC4_TEST_EMULATED_SLOW") == "1"
 LIGHT = FAST if SLOW else (FAST + " and not host_driver_three_set and not ring_restarts and not measurement_file and not force_energy_file"
                            " and not bitwise_reproducible and not impurity_hyper and not (forward_walking_vs_oracle and 3)"
-                           " and not (agrees_with_the_general and (256 or 512 or 160 or 100)) and not baseline_sizes and not is_bitwise")
+                           " and not (agrees_with_the_general and (256 or 512 or 160 or 100)) and not baseline_sizes and not is_bitwise"
+                           " and not branching_bookkeeping and not (upload_keeps_every_walker and 40000)")
 
 
 @pytest.fixture(scope="module")

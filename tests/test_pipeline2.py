@@ -239,3 +239,46 @@ def test_pair_hist_kernel_vs_general_estimator_and_oracle(port, N, L, bins, minx
         rs, rw = port.histogram(cfg, p, 0, bins)
         ref += rs
     assert _rel(sl, ref) < 1e-9
+
+
+@pytest.mark.parametrize("W", [2100, 40000])
+def test_scan_over_many_ctas_upload_keeps_every_walker(W):
+    """the scan needs several CTAs above 1024 walkers (40000: more CTAs than one warp of the finishing CTA sums -- round 2 lost
+    every walker beyond 32768 because the published totals were cleared while thread 0 was still adding them): the population
+    after an upload is the uploaded one, and a step without branching (svmc, main.cpp:393-395) keeps it"""
+    from qmc4_b200.system import System
+    cfg = cases.trap(2, walkers=W)
+    cfg["method"] = "svmc"
+    R = np.random.default_rng(W).normal(0, 1.0, size=(W, 6))
+    s = System.from_input(cfg)
+    s.upload(R)
+    assert s.info("global_population") == W
+    np.testing.assert_array_equal(s.download(), R)
+    s.step(2, 1)
+    assert s.block_results()["population"] == W and len(s.download()) == W
+    s.close()
+
+
+@pytest.mark.parametrize("W,pipeline", [(3000, 2), (3000, 1), (5300, 2), (40000, 2)])
+def test_scan_over_many_ctas_branching_bookkeeping(W, pipeline):
+    """branching across several scan CTAs: the new population is sum(nDescendants) (branching.cpp:16-63) and the walkers downloaded
+    afterwards are the accepted / rejected configurations in stable prefix-sum order"""
+    from qmc4_b200.system import System
+    cfg = cases.trap(2, walkers=W)
+    cfg["timeStep"] = 5e-2                       # a visible spread of nDescendants (0, 1, 2)
+    R = np.random.default_rng(W).normal(0, 1.0, size=(W, 6))
+    os.environ["QMC4_PIPELINE"] = str(pipeline)
+    try:
+        s = System.from_input(cfg)
+        s.upload(R)
+        tr = s.step_traced()
+        Rn = s.download()
+        b = s.block_results()
+        s.close()
+    finally:
+        os.environ.pop("QMC4_PIPELINE", None)
+    nd = tr["n_desc"]
+    assert tr["n_before"] == W and tr["n_after"] == nd.sum() == len(Rn) == b["population"]
+    assert set(np.unique(nd)) - {0, 1} and nd.min() >= 0             # branching did clone some walkers
+    moved = np.where(tr["accepted"][:, None] != 0, tr["Rprop"], R)
+    np.testing.assert_array_equal(Rn, np.repeat(moved, nd, axis=0))
