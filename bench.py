@@ -554,7 +554,7 @@ def main():
                                         "population": m2["population"], "gpu_launches": m2["launches"], "cuda_graph_replays": m2["graph_replays"],
                                         "roofline": rf, "kernel": r2["kernel"]}
                 if not args.no_cpu_baseline:
-                    sec[key]["cpu_baseline"] = cpu_reference_arm(r2["cfg"], seconds_budget=4.0)
+                    sec[key]["cpu_baseline"] = cpu_reference_arm(r2["cfg"], seconds_budget=10.0)
             except Exception as e:          # a secondary shape must never take the headline down
                 sec[key] = {"error": repr(e)[:300]}
         line["secondary"] = sec
