@@ -327,3 +327,32 @@ def test_forward_walking_needs_steps_below_record_steps(port):
     pops, ancs = cases.synthetic_genealogy(cfg, 3, 4, 1)
     with pytest.raises(Exception):
         port.forward_walking(cfg, pops, ancs, 0, 4, 4, 16)
+
+
+def test_pair_histogram_lower_bound(port):
+    """histogramAccumulator::accumulate (accumulators.h:117) has no lower bound: minx - dx < x < minx truncates to bin 0, anything
+    below writes before the array in the reference.  The restatement drops those samples (and so do the CUDA kernels): checked
+    against a numpy restatement of pairCorrelation.cpp:17-39 with that rule, on walkers that do contain pairs below minx"""
+    N, L, bins, minx = 20, 3.0, 16, 0.6
+    maxx = L / 2
+    cfg = cases.pbc(N, L, walkers=8, meas=[{"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": bins, "minx": minx, "maxx": maxx}])
+    R = np.random.default_rng(12).uniform(-L / 2, L / 2, size=(8, 3 * N))
+    sums, w = port.histogram(cfg, R, 0, bins)
+    dx = (maxx - minx) / bins
+    nf = 2 * L ** 3 / (dx * 4 * np.pi * N * N)
+    exp, below = np.zeros(bins), 0
+    for Rw in R:
+        x = Rw.reshape(3, N)
+        for i in range(N):
+            for j in range(i):
+                d = x[:, i] - x[:, j]
+                d -= L * np.round(d / L)
+                r = np.sqrt((d * d).sum())
+                if r < maxx:
+                    b = int((r - minx) / dx)          # C truncation
+                    if r < minx - dx:
+                        below += 1
+                    if b >= 0:
+                        exp[min(b, bins - 1)] += nf / r ** 2
+    assert below > 0 and w == len(R)
+    np.testing.assert_allclose(sums, exp, rtol=1e-12)
