@@ -72,10 +72,11 @@ def test_parity_suite_on_emulated_kernels(emu_lib, suite):
     assert " passed" in tail and "failed" not in tail, tail
 
 
-@pytest.mark.parametrize("nranks,N,wpr,wpw", [(2, 16, 24, ""), (8, 16, 6, "")] + ([(4, 40, 10, "2"), (8, 64, 6, "8")] if SLOW else []))
+@pytest.mark.parametrize("nranks,N,wpr,wpw", [(2, 16, 24, ""), (8, 16, 6, "")] + ([(4, 40, 10, "2"), (8, 64, 6, "8"), (2, 2, 1300, "")] if SLOW else []))
 def test_multirank_steps_and_rebalance_on_emulated_ranks(emu_lib, nranks, N, wpr, wpw):
     """ranks = threads over an in-process NCCL stand-in: global E_T / block results identical on every
-    rank, rebalance conserves the walker multiset and equalises the populations (ptools.cpp:93-161)"""
+    rank, rebalance conserves the walker multiset and equalises the populations (ptools.cpp:93-161).  The slow list adds
+    1300 walkers per rank: in-step migration (n_adjust) through the multi-CTA scan"""
     env = _env(emu_lib)
     env["QMC4_NCCL_LIB"] = os.path.join(EMU_DIR, "libnccl_emu.so")
     if wpw:
