@@ -128,6 +128,14 @@ def _tsan_inputs():
         "vmc_force_energy": dict(vmc, walkers=6, stepsPerBlock=3, nBlocks=2, correlationSteps=1),
         "generic_dipolar_rep": dict(cases.pbc(10, 5.2, walkers=6, jastrow=cases.DIPOLAR_REP), delta_walkers=2, timeStep=1e-3, **small),
         "structure_factor": dict(cases.structure_factor(), walkers=6, delta_walkers=2, **small),
+        # round-2 kernels: tournament pair kernel with a ragged last block + its fixed-point g(r) kernel, the packed small-system
+        # kernel, and a population that needs several scan CTAs (the finishing CTA of the scan once cleared the published totals
+        # while its thread 0 was still adding them: exactly the access pair tsan reports)
+        "pair_kernel_g_of_r": dict(cases.pbc(70, 4.1, walkers=6, meas=[{"kind": "pairCorrelation", "label": "pair", "sets": [0, 0], "bins": 50,
+                                                                         "minx": 0.1, "maxx": 2.05}]), delta_walkers=2, **small),
+        "small_trap": dict(cases.trap(5, walkers=12), delta_walkers=3, initialConditionGenerator={"lBox": [2.0, 2.0, 2.0]}, **small),
+        "scan_many_ctas": dict(cases.trap(2, walkers=1100), delta_walkers=100, initialConditionGenerator={"lBox": [2.0, 2.0, 2.0]},
+                               stepsPerBlock=2, nBlocks=1, correlationSteps=0),
     }
     return out
 
