@@ -33,3 +33,17 @@ def test_workloads_follow_the_baseline_configs():
         assert pairs == N * (N - 1) / 2 and nbytes == 96 * N + 48
         assert flops >= 64 * pairs
     assert bench.workload(2, 16384, 8)["walkers"] == 8 * 16384          # weak scaling: global target grows with the ranks
+
+
+def test_committed_workload_files_are_what_bench_feeds_both_arms():
+    """bench/configs/config<i>.json == bench.workload(i): the documents are fed unchanged to both arms"""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench as B
+    for c in (1, 2, 3, 4, 5):
+        ng = 8 if c == 5 else 1
+        want = json.loads(json.dumps(B.workload(c, B.DEFAULT_WALKERS[c], ng)))
+        got = json.load(open(os.path.join(ROOT, "bench", "configs", "config%d.json" % c)))
+        assert got == want, c
+    sv = json.load(open(os.path.join(ROOT, "bench", "configs", "config1_svmc.json")))
+    assert sv == dict(json.loads(json.dumps(B.workload(1, B.DEFAULT_WALKERS[1], 1))), method="svmc")
